@@ -1,0 +1,354 @@
+"""Python wrappers over the C-ABI kernels of libctta.so.
+
+torch is used for device memory and streams only; every arithmetic op on the hot path is a libctta kernel.
+All activations are channels-last: images [N, H, W, C], sequences [B, T, C], token matrices [M, C].
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (A_CONV1D, A_CONV2D, A_ROWS, ACT_GEGLU, ACT_LRELU, ACT_NONE, ACT_SILU, ACT_TANH, BF16, F16, F32,
+                   GemmDesc, check, lib)
+
+# 16-bit operand type of the tensor-core path.  fp16 (10-bit mantissa) is what keeps the UNet / VAE within the
+# 1e-2 rel-L2 tolerance against the fp32 reference (the reference's own bf16 autocast does not).
+OPERAND_DTYPE = torch.float16
+
+_DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+
+def _require_cuda(t):
+    if not t.is_cuda:
+        raise _lib.CttaError("consistencytta_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------ weight packing
+class PackedWeight:
+    """K-major 16-bit GEMM operand W[n, ntaps * c_pad] (+ fp32 bias) with the tap shifts of the implicit GEMM."""
+
+    def __init__(self, w16, bias, ntaps, c, n, d0, d1, out_stride=1, out_off=0):
+        self.w = w16
+        self.bias = bias
+        self.ntaps = ntaps
+        self.c = c
+        self.n = n
+        self.d0 = list(d0)
+        self.d1 = list(d1)
+        self.out_stride = out_stride
+        self.out_off = out_off
+
+
+def _pack_taps(w_ntc, dtype):
+    """w_ntc: [n, ntaps, c] fp32 -> [n, ntaps * c_pad] 16-bit, zero padded per tap to a multiple of 64."""
+    n, ntaps, c = w_ntc.shape
+    c_pad = round_up(c, 64)
+    out = torch.zeros(n, ntaps, c_pad, dtype=dtype, device=w_ntc.device)
+    out[:, :, :c] = w_ntc.to(dtype)
+    return out.reshape(n, ntaps * c_pad).contiguous()
+
+
+def _bias(b, n, device):
+    if b is None:
+        return None
+    return b.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def pack_linear(weight, bias=None, dtype=None, k_pad_to=None, n_pad_to=None):
+    """nn.Linear weight [n, k] (optionally zero padded to [n_pad_to, k_pad_to])."""
+    dtype = dtype or OPERAND_DTYPE
+    w = weight.detach().float()
+    n, k = w.shape
+    kp = k_pad_to or k
+    np_ = n_pad_to or n
+    wp = torch.zeros(np_, kp, device=w.device)
+    wp[:n, :k] = w
+    b = None
+    if bias is not None:
+        b = torch.zeros(np_, device=w.device)
+        b[:n] = bias.detach().float()
+    return PackedWeight(_pack_taps(wp[:, None, :], dtype), b, 1, kp, np_, [0], [0])
+
+
+def pack_conv2d(weight, bias=None, dtype=None):
+    """nn.Conv2d weight [cout, cin, kh, kw], stride 1, 'same' padding -> taps ordered (kh, kw)."""
+    dtype = dtype or OPERAND_DTYPE
+    w = weight.detach().float()
+    cout, cin, kh, kw = w.shape
+    w_ntc = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+    d0, d1 = [], []
+    for i in range(kh):
+        for j in range(kw):
+            d1.append(i - (kh - 1) // 2)
+            d0.append(j - (kw - 1) // 2)
+    return PackedWeight(_pack_taps(w_ntc, dtype), _bias(bias, cout, w.device), kh * kw, cin, cout, d0, d1)
+
+
+def pack_conv2d_im2col(weight, bias=None, dtype=None):
+    """3x3 conv weight for a pre-gathered A [M, 9 * cin] (stride-2 downsamplers): one tap, K = 9 * cin."""
+    dtype = dtype or OPERAND_DTYPE
+    w = weight.detach().float()
+    cout, cin, kh, kw = w.shape
+    w_k = w.permute(0, 2, 3, 1).reshape(cout, 1, kh * kw * cin)
+    return PackedWeight(_pack_taps(w_k, dtype), _bias(bias, cout, w.device), 1, kh * kw * cin, cout, [0], [0])
+
+
+def pack_conv1d(weight, bias=None, dilation=1, dtype=None):
+    """nn.Conv1d weight [cout, cin, k], stride 1, padding (k*d - d)/2 (hifigan/models.py:16-17)."""
+    dtype = dtype or OPERAND_DTYPE
+    w = weight.detach().float()
+    cout, cin, k = w.shape
+    w_ntc = w.permute(0, 2, 1).contiguous()
+    d0 = [(j - (k - 1) // 2) * dilation for j in range(k)]
+    return PackedWeight(_pack_taps(w_ntc, dtype), _bias(bias, cout, w.device), k, cin, cout, d0, [0] * k)
+
+
+def pack_conv_transpose1d(weight, bias, stride, padding, dtype=None):
+    """nn.ConvTranspose1d weight [cin, cout, k] -> one PackedWeight per output phase r in [0, stride).
+
+    y[t] = sum_{i*s + j - p = t} x[i] w[:, :, j].  With t + p = s*q + r:  y[s*q + r - p] = sum_m x[q - m] w[r + s*m],
+    i.e. phase r is a stride-1 conv over q with taps shifted by -m, written to output rows q*s + (r - p).
+    """
+    dtype = dtype or OPERAND_DTYPE
+    w = weight.detach().float()
+    cin, cout, k = w.shape
+    phases = []
+    for r in range(stride):
+        js = list(range(r, k, stride))
+        w_ntc = torch.stack([w[:, :, j].t() for j in js], dim=1).contiguous()  # [cout, ntaps, cin]
+        d0 = [-m for m in range(len(js))]
+        phases.append(PackedWeight(_pack_taps(w_ntc, dtype), _bias(bias, cout, w.device), len(js), cin, cout, d0,
+                                   [0] * len(js), out_stride=stride, out_off=r - padding))
+    return phases
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def gemm(a, pw, mode=A_ROWS, n_img=1, h=1, w=None, rows_per_img=None, a_ld=None, out=None, out_ld=None,
+         out_rows_per_img=None, residual=None, res_ld=None, rowadd=None, rowadd_rows=1, act=ACT_NONE, act_slope=0.0,
+         accumulate=False, out_scale=1.0, out2=None, out2_ld=None, act2=ACT_NONE, act2_slope=0.0, use_bias=True):
+    """Launches ctta_gemm.  `a` is a 16-bit channels-last tensor; shapes are given explicitly by the caller."""
+    _require_cuda(a)
+    d = GemmDesc()
+    d.a = a.data_ptr()
+    d.a_mode = mode
+    d.ab_dtype = _DT[a.dtype]
+    assert pw.w.dtype == a.dtype, "operand dtype mismatch"
+    d.c = pw.c
+    d.a_ld = a_ld if a_ld is not None else a.shape[-1]
+    d.n_img = n_img
+    d.h = h
+    d.w = w if w is not None else (a.shape[0] if mode == A_ROWS else 0)
+    if rows_per_img is None:
+        rows_per_img = d.h * d.w
+    d.rows_per_img = rows_per_img
+    d.ntaps = pw.ntaps
+    for j in range(pw.ntaps):
+        d.tap_d0[j] = pw.d0[j]
+        d.tap_d1[j] = pw.d1[j]
+    d.wgt = pw.w.data_ptr()
+    d.n = pw.n
+    d.bias = pw.bias.data_ptr() if (use_bias and pw.bias is not None) else None
+    if rowadd is not None:
+        d.rowadd = rowadd.data_ptr()
+        d.rowadd_ld = rowadd.stride(0)
+        d.rowadd_rows = rowadd_rows
+    d.act = act
+    d.act_slope = act_slope
+    if residual is not None:
+        d.residual = residual.data_ptr()
+        d.res_dtype = _DT[residual.dtype]
+        d.res_ld = res_ld if res_ld is not None else residual.shape[-1]
+    d.accumulate = 1 if accumulate else 0
+    d.out_scale = out_scale
+    if out is not None:
+        d.out = out.data_ptr()
+        d.out_dtype = _DT[out.dtype]
+        d.out_ld = out_ld if out_ld is not None else out.shape[-1]
+    if out2 is not None:
+        d.out2 = out2.data_ptr()
+        d.out2_ld = out2_ld if out2_ld is not None else out2.shape[-1]
+        d.act2 = act2
+        d.act2_slope = act2_slope
+    d.out_rows_per_img = out_rows_per_img if out_rows_per_img is not None else rows_per_img
+    d.out_stride = pw.out_stride
+    d.out_off = pw.out_off
+    check(lib().ctta_gemm(C.byref(d), _stream()))
+    return out if out is not None else out2
+
+
+def linear(a, pw, **kw):
+    """a: [M, K] 16-bit."""
+    return gemm(a, pw, mode=A_ROWS, n_img=1, h=1, w=a.shape[0], rows_per_img=a.shape[0], a_ld=a.stride(0), **kw)
+
+
+def conv2d(a, pw, **kw):
+    """a: [N, H, W, C] 16-bit channels-last; 'same' conv given by pw's taps."""
+    n, h, w, _ = a.shape
+    return gemm(a, pw, mode=A_CONV2D, n_img=n, h=h, w=w, rows_per_img=h * w, a_ld=a.stride(2), **kw)
+
+
+def conv1d(a, pw, rows_per_img=None, out_rows_per_img=None, **kw):
+    """a: [B, T, C] 16-bit channels-last."""
+    b, t, _ = a.shape
+    rp = rows_per_img if rows_per_img is not None else t
+    return gemm(a, pw, mode=A_CONV1D, n_img=b, h=1, w=t, rows_per_img=rp,
+                out_rows_per_img=out_rows_per_img if out_rows_per_img is not None else rp, a_ld=a.stride(1), **kw)
+
+
+def conv_transpose1d(a, phases, t_out, **kw):
+    """a: [B, T, C]; phases from pack_conv_transpose1d; writes every output row exactly once."""
+    b, t, _ = a.shape
+    res = None
+    for pw in phases:
+        # q ranges over [0, ceil((t_out - out_off) / stride)) — rows mapping outside [0, t_out) are dropped
+        q = (t_out - pw.out_off + pw.out_stride - 1) // pw.out_stride
+        res = conv1d(a, pw, rows_per_img=max(q, 1), out_rows_per_img=t_out, **kw)
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ norms
+def groupnorm_stats(x, groups, x2=None, stats=None):
+    """x: [N, H, W, C] (fp32 or 16-bit), optional x2 [N, H, W, C2] concatenated on channels -> stats [N, G, 2]."""
+    _require_cuda(x)
+    n, h, w, c = x.shape
+    c2 = x2.shape[-1] if x2 is not None else 0
+    if stats is None:
+        stats = torch.empty(n, groups, 2, device=x.device, dtype=torch.float32)
+    check(lib().ctta_groupnorm_stats(_ptr(x), _DT[x.dtype], c, x.stride(2), _ptr(x2), c2,
+                                     x2.stride(2) if x2 is not None else 0, n, h * w, groups, _ptr(stats), _stream()))
+    return stats
+
+
+def groupnorm_apply(x, groups, stats, gamma, beta, eps=1e-5, act=ACT_SILU, x2=None, upsample=False, out=None, raw_out=None,
+                    out_dtype=None):
+    """Normalise (+SiLU) -> 16-bit operand [N, H', W', C+C2]; stats=None: plain cast/concat/upsample."""
+    _require_cuda(x)
+    n, h, w, c = x.shape
+    c2 = x2.shape[-1] if x2 is not None else 0
+    s = 2 if upsample else 1
+    if out is None:
+        out = torch.empty(n, h * s, w * s, c + c2, device=x.device, dtype=out_dtype or OPERAND_DTYPE)
+    check(lib().ctta_groupnorm_apply(_ptr(x), _DT[x.dtype], c, x.stride(2), _ptr(x2), c2,
+                                     x2.stride(2) if x2 is not None else 0, n, h, w, groups, _ptr(stats), _ptr(gamma),
+                                     _ptr(beta), eps, act, 1 if upsample else 0, _ptr(out), _DT[out.dtype], out.stride(2),
+                                     _ptr(raw_out), raw_out.stride(2) if raw_out is not None else 0, _stream()))
+    return out
+
+
+def layernorm(x, d, gamma, beta, eps, out=None):
+    """x: fp32 [M, ld] (first d columns valid) -> 16-bit [M, ld] with pad columns zero."""
+    _require_cuda(x)
+    m, ld = x.shape
+    if out is None:
+        out = torch.empty(m, ld, device=x.device, dtype=OPERAND_DTYPE)
+    check(lib().ctta_layernorm(_ptr(x), m, d, x.stride(0), _ptr(gamma), _ptr(beta), eps, _ptr(out), _DT[out.dtype],
+                               out.stride(0), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def attention(q, k, v, scale, kv_len=None, out=None):
+    """q: [B, Lq, H, D], k/v: [B, Lk, H, D] 16-bit views (last dim contiguous, head stride = D)."""
+    _require_cuda(q)
+    b, lq, h, dh = q.shape
+    lk = k.shape[1]
+    if out is None:
+        out = torch.empty(b, lq, h, dh, device=q.device, dtype=q.dtype)
+    for t in (q, k, v, out):
+        assert t.stride(3) == 1 and t.stride(2) == dh
+    check(lib().ctta_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _DT[q.dtype], b, h, lq, lk, dh,
+                               q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                               out.stride(0), out.stride(1), _ptr(kv_len), scale, _stream()))
+    return out
+
+
+def softmax_rows(x, scale, out=None):
+    """x: fp32 [rows, cols] -> 16-bit softmax(scale * x) rows."""
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty(rows, cols, device=x.device, dtype=OPERAND_DTYPE)
+    check(lib().ctta_softmax_rows(_ptr(x), rows, cols, x.stride(0), scale, _ptr(out), _DT[out.dtype], out.stride(0),
+                                  _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ misc
+def im2col_s2(x):
+    n, h, w, c = x.shape
+    assert x.is_contiguous()
+    out = torch.empty(n * (h // 2) * (w // 2), 9 * c, device=x.device, dtype=x.dtype)
+    check(lib().ctta_im2col_s2(_ptr(x), n, h, w, c, _ptr(out), _stream()))
+    return out
+
+
+def nchw_to_nhwc(x, dtype=torch.float32, scale=1.0, c_pad=None):
+    """fp32 NCHW -> channels-last [N, H, W, c_pad] (zero padded channels)."""
+    _require_cuda(x)
+    x = x.contiguous().float()
+    n, c, h, w = x.shape
+    cp = c_pad or c
+    out = (torch.zeros if cp != c else torch.empty)(n, h, w, cp, device=x.device, dtype=dtype)
+    check(lib().ctta_nchw_to_nhwc(_ptr(x), n, c, h * w, _ptr(out), _DT[dtype], cp, scale, _stream()))
+    return out
+
+
+def nhwc_to_nchw(x, c=None):
+    """fp32 channels-last [N, H, W, ld] -> fp32 NCHW [N, c, H, W]."""
+    n, h, w, ld = x.shape
+    c = c or ld
+    out = torch.empty(n, c, h, w, device=x.device, dtype=torch.float32)
+    check(lib().ctta_nhwc_to_nchw(_ptr(x), n, c, h * w, x.stride(2), _ptr(out), _stream()))
+    return out
+
+
+def time_features(t, w, gw):
+    b = t.shape[0]
+    tf = torch.empty(b, 256, device=t.device, dtype=torch.float32)
+    gf = torch.empty(b, gw.shape[0] * 2, device=t.device, dtype=torch.float32)
+    check(lib().ctta_time_features(_ptr(t), _ptr(w), _ptr(gw), b, _ptr(tf), _ptr(gf), _stream()))
+    return tf, gf
+
+
+def small_linear(x, weight, bias, act_in=ACT_NONE, act_out=ACT_NONE, accumulate=False, out=None):
+    m, k = x.shape
+    n = weight.shape[0]
+    if out is None:
+        out = torch.empty(m, n, device=x.device, dtype=torch.float32)
+    check(lib().ctta_small_linear(_ptr(x), m, k, _ptr(weight), _ptr(bias), n, act_in, act_out, 1 if accumulate else 0,
+                                  _ptr(out), _stream()))
+    return out
+
+
+def wave_to_int16(wav, minmax=None):
+    """Batch-global centring + int16 truncation (hifigan/utilities.py:84-86). Returns (int16 tensor, minmax)."""
+    numel = wav.numel()
+    if minmax is None:
+        minmax = torch.empty(2, device=wav.device, dtype=torch.float32)
+        check(lib().ctta_wave_minmax(_ptr(wav), numel, _ptr(minmax), _stream()))
+    out = torch.empty(wav.shape, device=wav.device, dtype=torch.int16)
+    check(lib().ctta_wave_to_int16(_ptr(wav), numel, _ptr(minmax), _ptr(out), _stream()))
+    return out, minmax
+
+
+def cfg_mix(x, s):
+    half = x.shape[0] // 2
+    out = torch.empty((half,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+    check(lib().ctta_cfg_mix(_ptr(x), out.numel(), s, _ptr(out), _stream()))
+    return out
+
+
+def launch_count():
+    return int(lib().ctta_launch_count())

@@ -1,0 +1,184 @@
+/*
+ * libctta — C-ABI of the B200 (sm_100a) kernels behind the ConsistencyTTA single-step generation path
+ * (guided UNet forward -> AudioLDM VAE decode -> HiFi-GAN vocoder).
+ *
+ * The reference (Bai-YT/ConsistencyTTA) has no FFI layer: its boundary is the Python nn.Module API
+ * (SURVEY.md 8b).  The Python modules in consistencytta_b200/ keep that API and call these entry points
+ * through ctypes with raw device pointers; every function replaces one family of ATen call sites of the
+ * reference, cited per function as  <reference file>:<line>.
+ *
+ * Conventions: every function returns 0 on success or a negative ctta_status; ctta_last_error() gives the
+ * message of the last failure on the calling thread.  All pointers are DEVICE pointers unless named host_*.
+ * No function allocates, synchronises or touches a stream other than the `stream` argument (a cudaStream_t
+ * passed as void*).  Activations are channels-last: images [N, H, W, C], sequences [B, T, C], tokens [M, C].
+ */
+#ifndef CTTA_H_
+#define CTTA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  CTTA_OK = 0,
+  CTTA_ERR_INVALID = -1,   /* bad argument (shape, alignment, enum) */
+  CTTA_ERR_CUDA = -2,      /* CUDA runtime / driver error */
+  CTTA_ERR_UNSUPPORTED = -3
+} ctta_status;
+
+typedef enum { CTTA_F32 = 0, CTTA_F16 = 1, CTTA_BF16 = 2 } ctta_dtype;
+
+/* epilogue activations */
+typedef enum {
+  CTTA_ACT_NONE = 0,
+  CTTA_ACT_SILU = 1,
+  CTTA_ACT_GEGLU = 2, /* columns interleaved (value, gate): out[:, j] = v[2j] * gelu_erf(v[2j+1]); out has N/2 cols */
+  CTTA_ACT_TANH = 3,
+  CTTA_ACT_LRELU = 4
+} ctta_act;
+
+/* how the A operand (activations) is addressed */
+typedef enum {
+  CTTA_A_ROWS = 0,   /* A is a row-major matrix [M, K] (Linear, 1x1 conv, pre-gathered im2col)            */
+  CTTA_A_CONV1D = 1, /* A is [B, T, C]; tap j reads rows t + tap_d0[j] (zero outside [0, T))              */
+  CTTA_A_CONV2D = 2  /* A is [N, H, W, C]; tap j reads pixel (h + tap_d1[j], w + tap_d0[j]), zero padded  */
+} ctta_a_mode;
+
+#define CTTA_MAX_TAPS 16
+
+const char* ctta_last_error(void);
+int ctta_version(void);
+/* number of kernels launched by this library since load (all threads); used for bench.py's gpu_launches */
+long long ctta_launch_count(void);
+
+/*
+ * Implicit-GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators, persistent, warp-specialised):
+ *     acc[m, n] = sum_{tap j} sum_{c < C} A(m shifted by tap j, c) * W[n, j * c_pad + c]
+ *     v   = act(acc + bias[n] + rowadd[img(m), n])
+ *     v   = (v + residual[orow(m), n] + (accumulate ? out[orow(m), n] : 0)) * out_scale
+ *     out[orow(m), n] = v ;   out2[orow(m), n] = f16/bf16( act2(v) )      (out2 optional)
+ * Replaces, in the reference: F.conv2d 3x3/1x1 (diffusers/models/resnet.py:570,590,593,157;
+ * unet_2d_condition_guided.py:863,940; audioldm/variational_autoencoder/modules.py:56,159,167,173,207-209,228,
+ * 658,680; autoencoder.py:99), F.linear (attention_processor.py:1110-1135; transformer_2d.py:267,295;
+ * attention.py:378,431), F.conv1d and F.conv_transpose1d (audioldm/hifigan/models.py:59,61,102,105,114),
+ * plus the elementwise ops fused as epilogue (resnet.py:573-576,595; attention.py:305-332,432;
+ * hifigan/models.py:58-62,104,108-115).
+ */
+typedef struct {
+  /* ---- A operand (16-bit, channels-last) */
+  const void* a;
+  int32_t a_mode;     /* ctta_a_mode */
+  int32_t ab_dtype;   /* CTTA_F16 or CTTA_BF16 (A and W) */
+  int32_t c;          /* channels (K per tap) actually present in A */
+  int32_t a_ld;       /* elements between consecutive rows / pixels / time steps of A (>= c, multiple of 8) */
+  int32_t n_img;      /* ROWS: 1;  CONV1D: B;  CONV2D: N */
+  int32_t h, w;       /* CONV2D: H, W;  CONV1D: h = 1, w = T (input length);  ROWS: h = 1, w = M */
+  int32_t rows_per_img; /* logical GEMM rows per image: ROWS: M; CONV1D: number of output positions computed
+                           (before the output mapping below); CONV2D: H * W */
+  /* ---- taps */
+  int32_t ntaps;
+  int16_t tap_d0[CTTA_MAX_TAPS]; /* shift along w / t */
+  int16_t tap_d1[CTTA_MAX_TAPS]; /* shift along h */
+  /* ---- W operand: [n, ntaps * c_pad] row-major 16-bit, c_pad = c rounded up to 64, zero padded */
+  const void* wgt;
+  int32_t n;          /* output channels (GEMM N, before GEGLU halving) */
+  /* ---- epilogue */
+  const float* bias;      /* [n] or NULL */
+  const float* rowadd;    /* [n_img_rowadd, rowadd_ld] fp32 or NULL; indexed by img(m) = m / rowadd_rows */
+  int32_t rowadd_ld;
+  int32_t rowadd_rows;    /* logical rows sharing one rowadd row (e.g. H*W for a time embedding) */
+  int32_t act;            /* ctta_act */
+  float act_slope;        /* LRELU slope */
+  const void* residual;   /* [*, res_ld] or NULL */
+  int32_t res_dtype;      /* CTTA_F32 / CTTA_F16 / CTTA_BF16 */
+  int32_t res_ld;
+  int32_t accumulate;     /* add the previous contents of out */
+  float out_scale;
+  void* out;              /* may be NULL when only out2 is wanted */
+  int32_t out_dtype;
+  int32_t out_ld;
+  void* out2;             /* optional 16-bit second output (dtype = ab_dtype) */
+  int32_t out2_ld;
+  int32_t act2;           /* CTTA_ACT_NONE / SILU / LRELU applied to v for out2 */
+  float act2_slope;
+  /* ---- output row mapping: logical row r of image i goes to row  i * out_rows_per_img + r * out_stride + out_off,
+   *      and is dropped unless 0 <= r * out_stride + out_off < out_rows_per_img (transposed-conv phases). */
+  int32_t out_rows_per_img;
+  int32_t out_stride;
+  int32_t out_off;
+} ctta_gemm_desc;
+
+int ctta_gemm(const ctta_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Bandwidth-bound kernels (vectorised, coalesced, warp-shuffle reductions).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* GroupNorm raw moments over channels-last input x[n_img, hw, c] (row stride ld): (sum x, sum x^2) per
+ * (image, group).  Optional second source x2 (c2 channels, row stride ld2) is the channel-concatenated skip tensor
+ * (torch.cat at diffusers/models/unet_2d_blocks.py:2032,2134).  stats = float[n_img, groups, 2] (zeroed here).
+ * Reference: F.group_norm at resnet.py:555,581; transformer_2d.py:259; unet_2d_condition_guided.py:938;
+ * audioldm/variational_autoencoder/modules.py:38-41. */
+int ctta_groupnorm_stats(const void* x, int32_t x_dtype, int32_t c, int32_t ld, const void* x2, int32_t c2,
+                         int32_t ld2, int32_t n_img, int32_t hw, int32_t groups, float* stats, void* stream);
+
+/* y = act((x - mean) * rsqrt(var + eps) * gamma + beta), mean/var from the raw moments, written 16-bit, channels-last, optionally nearest-upsampled 2x
+ * (F.interpolate at resnet.py:146, modules.py:54) — the operand of the following conv/linear.
+ * With stats == NULL the normalisation is skipped (plain cast / concat / upsample).  act: NONE or SILU.
+ * Optional raw 16-bit copy of the (concatenated) input into raw_out (operand of the 1x1 shortcut conv). */
+int ctta_groupnorm_apply(const void* x, int32_t x_dtype, int32_t c, int32_t ld, const void* x2, int32_t c2,
+                         int32_t ld2, int32_t n_img, int32_t h, int32_t w, int32_t groups, const float* stats,
+                         const float* gamma, const float* beta, float eps, int32_t act, int32_t upsample2x,
+                         void* y, int32_t y_dtype, int32_t y_ld, void* raw_out, int32_t raw_ld, void* stream);
+
+/* LayerNorm over the first d of ld columns of fp32 x[m, ld]; writes 16-bit y[m, y_ld] (pad columns zeroed).
+ * Reference: F.layer_norm at diffusers/models/attention.py:293,309,322. */
+int ctta_layernorm(const float* x, int32_t m, int32_t d, int32_t ld, const float* gamma, const float* beta,
+                   float eps, void* y, int32_t y_dtype, int32_t y_ld, void* stream);
+
+/* Fused flash-style attention, head_dim padded to 64: q[b, lq, heads, 64] etc. given as element strides.
+ * kv_len[b] (may be NULL) is the number of valid keys per batch row — the reference's additive -10000 bias on
+ * padded text tokens (unet_2d_condition_guided.py:793-795) underflows to exactly 0 weight in fp32.
+ * Reference: F.scaled_dot_product_attention at attention_processor.py:1127-1129; bmm+softmax at
+ * audioldm/variational_autoencoder/modules.py:216-225 (heads = 1, d = 512 handled as 8 x 64 chunks). */
+int ctta_attention(const void* q, const void* k, const void* v, void* o, int32_t dtype, int32_t batch,
+                   int32_t heads, int32_t lq, int32_t lk, int32_t head_dim, int64_t q_bs, int64_t q_ls,
+                   int64_t k_bs, int64_t k_ls, int64_t v_bs, int64_t v_ls, int64_t o_bs, int64_t o_ls,
+                   const int32_t* kv_len, float scale, void* stream);
+
+/* y[r, :] = softmax(scale * x[r, :]) for fp32 scores x[rows, ld] -> 16-bit probabilities (VAE AttnBlock,
+ * audioldm/variational_autoencoder/modules.py:217-218; scores and P.V run through ctta_gemm). */
+int ctta_softmax_rows(const float* x, int32_t rows, int32_t cols, int64_t ld, float scale, void* y, int32_t y_dtype,
+                      int64_t y_ld, void* stream);
+
+/* Gather for the three stride-2 3x3 convs (resnet.py:206): x[n, h, w, c] 16-bit -> a[n*(h/2)*(w/2), 9*c]. */
+int ctta_im2col_s2(const void* x, int32_t n_img, int32_t h, int32_t w, int32_t c, void* a, void* stream);
+
+/* NCHW fp32 <-> channels-last conversions at the module boundary. dst 16-bit or fp32. */
+int ctta_nchw_to_nhwc(const float* x, int32_t n_img, int32_t c, int32_t hw, void* y, int32_t y_dtype, int32_t y_ld,
+                      float scale, void* stream);
+int ctta_nhwc_to_nchw(const float* x, int32_t n_img, int32_t c, int32_t hw, int32_t ld, float* y, void* stream);
+
+/* Timestep + guidance embedding front end (embeddings.py:25-65,222-249; unet_2d_condition_guided.py:803-816):
+ * t_feat[b, 256] = [cos(t f_i), sin(t f_i)], g_feat[b, 1024] = [cos(2 pi w W), sin(2 pi w W)]. */
+int ctta_time_features(const float* t, const float* w, const float* gw, int32_t batch, float* t_feat, float* g_feat,
+                       void* stream);
+/* Small-M fp32 linear: y[m, n] = act_in(x)[m, k] @ W[n, k]^T + b (+ y if accumulate). act_in / act_out: NONE or SILU.
+ * For the embedding MLPs and the 22 time_emb_proj GEMVs batched as one call (embeddings.py:193-198; resnet.py:573). */
+int ctta_small_linear(const float* x, int32_t m, int32_t k, const float* wgt, const float* bias, int32_t n,
+                      int32_t act_in, int32_t act_out, int32_t accumulate, float* y, void* stream);
+
+/* Waveform post-processing (audioldm/hifigan/utilities.py:84-86): batch-global min/max, centre, * 32768,
+ * truncate toward zero to int16 (numpy astype semantics incl. wrap-around). minmax = float[2] scratch. */
+int ctta_wave_minmax(const float* wav, int64_t numel, float* minmax, void* stream);
+int ctta_wave_to_int16(const float* wav, int64_t numel, const float* minmax, int16_t* out, void* stream);
+
+/* (1 - s) * uncond + s * cond on the two batch halves (models/audio_consistency_model.py:453-456). */
+int ctta_cfg_mix(const float* x, int64_t half_numel, float s, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTTA_H_ */

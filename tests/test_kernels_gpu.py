@@ -1,0 +1,253 @@
+"""Per-kernel parity: every libctta kernel (called through the C-ABI via ctypes) against the same op in plain
+PyTorch fp32 on identical inputs.  Operands are pre-rounded to fp16 so the comparison isolates the kernel."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from consistencytta_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+DT = ops.OPERAND_DTYPE
+
+
+def rel(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def r16(x):
+    return x.to(DT).float()
+
+
+@pytest.mark.parametrize("m,k,n", [(300, 256, 320), (128, 64, 16), (1000, 1024, 8), (40000, 256, 256), (77, 320, 1280)])
+def test_linear(m, k, n):
+    torch.manual_seed(0)
+    a = r16(torch.randn(m, k, device=DEV))
+    w = r16(torch.randn(n, k, device=DEV) / math.sqrt(k))
+    b = torch.randn(n, device=DEV)
+    res = torch.randn(m, n, device=DEV)
+    pw = ops.pack_linear(w, b)
+    out = torch.empty(m, n, device=DEV)
+    ops.linear(a.to(DT), pw, out=out, residual=res)
+    ref = a @ w.t() + b + res
+    assert rel(out, ref) < 2e-5
+    # 16-bit output, no residual, padded K (k_pad_to) and SiLU second output
+    out16 = torch.empty(m, n, device=DEV, dtype=DT)
+    ops.linear(a.to(DT), pw, out=out16)
+    assert rel(out16, a @ w.t() + b) < 1e-3
+
+
+def test_linear_geglu():
+    torch.manual_seed(1)
+    m, k, d = 500, 256, 1024
+    a = r16(torch.randn(m, k, device=DEV))
+    w = r16(torch.randn(2 * d, k, device=DEV) / math.sqrt(k))
+    b = torch.randn(2 * d, device=DEV)
+    # interleave (value, gate)
+    wi = torch.stack([w[:d], w[d:]], dim=1).reshape(2 * d, k)
+    bi = torch.stack([b[:d], b[d:]], dim=1).reshape(2 * d)
+    pw = ops.pack_linear(wi, bi)
+    out = torch.empty(m, d, device=DEV, dtype=DT)
+    ops.linear(a.to(DT), pw, out=out, act=ops.ACT_GEGLU)
+    h = a @ w.t() + b
+    ref = h[:, :d] * F.gelu(h[:, d:])
+    assert rel(out, ref) < 1e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 16, 64, 128), (3, 256, 16, 8, 256), (1, 64, 4, 192, 8),
+                                            (5, 32, 2, 128, 64), (1, 128, 64, 128, 1), (2, 16, 32, 320, 512)])
+def test_conv2d_3x3(n, h, w, cin, cout):
+    torch.manual_seed(2)
+    x = r16(torch.randn(n, cin, h, w, device=DEV))
+    wt = r16(torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(9 * cin))
+    b = torch.randn(cout, device=DEV)
+    temb = torch.randn(n, cout, device=DEV)
+    ref = F.conv2d(x, wt, b, padding=1) + temb[:, :, None, None]
+    pw = ops.pack_conv2d(wt, b)
+    cp = ops.round_up(cin, 8)
+    a = torch.zeros(n, h, w, cp, device=DEV, dtype=DT)
+    a[..., :cin] = x.permute(0, 2, 3, 1)
+    ld = ops.round_up(cout, 8) if cout >= 8 else cout
+    out = torch.zeros(n, h, w, ld, device=DEV)
+    ops.conv2d(a, pw, out=out, rowadd=temb, rowadd_rows=h * w)
+    assert rel(out[..., :cout].permute(0, 3, 1, 2), ref) < 2e-5
+
+
+def test_conv2d_1x1_residual_out2():
+    torch.manual_seed(3)
+    n, h, w, cin, cout = 2, 64, 4, 256, 128
+    x = r16(torch.randn(n, cin, h, w, device=DEV))
+    wt = r16(torch.randn(cout, cin, 1, 1, device=DEV) / math.sqrt(cin))
+    b = torch.randn(cout, device=DEV)
+    res = torch.randn(n, h, w, cout, device=DEV)
+    ref = (F.conv2d(x, wt, b).permute(0, 2, 3, 1) + res) * 0.5
+    pw = ops.pack_conv2d(wt, b)
+    a = x.permute(0, 2, 3, 1).contiguous().to(DT)
+    out = torch.empty(n, h, w, cout, device=DEV)
+    out2 = torch.empty(n, h, w, cout, device=DEV, dtype=DT)
+    ops.conv2d(a, pw, out=out, residual=res, out_scale=0.5, out2=out2, act2=ops.ACT_SILU)
+    assert rel(out, ref) < 2e-5
+    assert rel(out2, F.silu(ref)) < 1e-3
+
+
+@pytest.mark.parametrize("k,dil,c,t", [(3, 1, 64, 300), (7, 3, 128, 5121), (11, 5, 32, 1000), (7, 1, 64, 129)])
+def test_conv1d(k, dil, c, t):
+    torch.manual_seed(4)
+    bsz = 2
+    x = r16(torch.randn(bsz, c, t, device=DEV))
+    wt = r16(torch.randn(c, c, k, device=DEV) / math.sqrt(k * c))
+    b = torch.randn(c, device=DEV)
+    ref = F.conv1d(F.leaky_relu(x, 0.1), wt, b, dilation=dil, padding=(k * dil - dil) // 2)
+    pw = ops.pack_conv1d(wt, b, dilation=dil)
+    a = F.leaky_relu(x, 0.1).permute(0, 2, 1).contiguous().to(DT)
+    xs = torch.randn(bsz, t, c, device=DEV)
+    out = xs.clone()
+    out2 = torch.empty(bsz, t, c, device=DEV, dtype=DT)
+    res = torch.randn(bsz, t, c, device=DEV)
+    ops.conv1d(a, pw, out=out, residual=res, accumulate=True, out_scale=1 / 3, out2=out2, act2=ops.ACT_LRELU,
+               act2_slope=0.1)
+    # a is rounded to fp16 after lrelu; recompute the reference from it
+    ref = F.conv1d(a.float().permute(0, 2, 1), wt, b, dilation=dil, padding=(k * dil - dil) // 2)
+    full = (ref.permute(0, 2, 1) + res + xs) / 3
+    assert rel(out, full) < 2e-5
+    assert rel(out2, F.leaky_relu(full, 0.1)) < 1e-3
+
+
+@pytest.mark.parametrize("k,s,cin,cout,t", [(16, 5, 128, 64, 50), (16, 4, 64, 32, 131), (8, 2, 64, 64, 200),
+                                            (4, 2, 64, 32, 257)])
+def test_conv_transpose1d(k, s, cin, cout, t):
+    torch.manual_seed(5)
+    bsz = 2
+    p = (k - s) // 2
+    x = r16(torch.randn(bsz, cin, t, device=DEV))
+    wt = r16(torch.randn(cin, cout, k, device=DEV) / math.sqrt(k * cin))
+    b = torch.randn(cout, device=DEV)
+    ref = F.conv_transpose1d(x, wt, b, stride=s, padding=p)
+    t_out = ref.shape[-1]
+    assert t_out == (t - 1) * s - 2 * p + k
+    phases = ops.pack_conv_transpose1d(wt, b, s, p)
+    a = x.permute(0, 2, 1).contiguous().to(DT)
+    out = torch.full((bsz, t_out, cout), float("nan"), device=DEV)
+    ops.conv_transpose1d(a, phases, t_out, out=out)
+    assert not torch.isnan(out).any()
+    assert rel(out.permute(0, 2, 1), ref) < 2e-5
+
+
+def test_im2col_s2_conv():
+    torch.manual_seed(6)
+    n, h, w, c, cout = 2, 32, 8, 64, 96
+    x = r16(torch.randn(n, c, h, w, device=DEV))
+    wt = r16(torch.randn(cout, c, 3, 3, device=DEV) / math.sqrt(9 * c))
+    b = torch.randn(cout, device=DEV)
+    ref = F.conv2d(x, wt, b, stride=2, padding=1)
+    a = ops.im2col_s2(x.permute(0, 2, 3, 1).contiguous().to(DT))
+    pw = ops.pack_conv2d_im2col(wt, b)
+    out = torch.empty(a.shape[0], cout, device=DEV)
+    ops.linear(a, pw, out=out)
+    assert rel(out.reshape(n, h // 2, w // 2, cout).permute(0, 3, 1, 2), ref) < 2e-5
+
+
+@pytest.mark.parametrize("n,h,w,c,c2,g", [(2, 64, 4, 256, 0, 32), (3, 32, 16, 512, 256, 32), (1, 128, 64, 128, 0, 32)])
+def test_groupnorm(n, h, w, c, c2, g):
+    torch.manual_seed(7)
+    x = torch.randn(n, h, w, c, device=DEV) * 2 + 0.5
+    x2 = torch.randn(n, h, w, c2, device=DEV) if c2 else None
+    gamma = torch.randn(c + c2, device=DEV)
+    beta = torch.randn(c + c2, device=DEV)
+    xc = torch.cat([x, x2], -1) if c2 else x
+    ref = F.silu(F.group_norm(xc.permute(0, 3, 1, 2), g, gamma, beta, eps=1e-6)).permute(0, 2, 3, 1)
+    st = ops.groupnorm_stats(x, g, x2=x2)
+    raw = torch.empty(n, h, w, c + c2, device=DEV, dtype=DT)
+    y = ops.groupnorm_apply(x, g, st, gamma, beta, eps=1e-6, x2=x2, raw_out=raw)
+    assert rel(y, ref) < 1e-3
+    assert rel(raw, xc) < 1e-3
+    yu = ops.groupnorm_apply(x, g, st, gamma, beta, eps=1e-6, x2=x2, upsample=True)
+    refu = ref.repeat_interleave(2, 1).repeat_interleave(2, 2)
+    assert rel(yu, refu) < 1e-3
+    # plain cast path
+    yc = ops.groupnorm_apply(x, g, None, None, None, act=ops.ACT_NONE, x2=x2)
+    assert rel(yc, xc) < 1e-3
+
+
+@pytest.mark.parametrize("m,d", [(1000, 255), (77, 510), (300, 1020)])
+def test_layernorm(m, d):
+    torch.manual_seed(8)
+    ld = ops.round_up(d, 64)
+    x = torch.zeros(m, ld, device=DEV)
+    x[:, :d] = torch.randn(m, d, device=DEV) * 3 + 1
+    gamma = torch.randn(d, device=DEV)
+    beta = torch.randn(d, device=DEV)
+    gp = torch.zeros(ld, device=DEV)
+    bp = torch.zeros(ld, device=DEV)
+    gp[:d] = gamma
+    bp[:d] = beta
+    y = ops.layernorm(x, d, gp, bp, 1e-5)
+    ref = F.layer_norm(x[:, :d], (d,), gamma, beta, 1e-5)
+    assert rel(y[:, :d], ref) < 1e-3
+    assert (y[:, d:] == 0).all()
+
+
+@pytest.mark.parametrize("b,h,lq,lk,masked", [(2, 5, 256, 256, False), (1, 10, 1024, 1024, False),
+                                              (3, 20, 64, 32, True), (2, 5, 4096, 77, True), (2, 4, 100, 200, False)])
+def test_attention(b, h, lq, lk, masked):
+    torch.manual_seed(9)
+    d = 64
+    q = r16(torch.randn(b, lq, h, d, device=DEV))
+    k = r16(torch.randn(b, lk, h, d, device=DEV))
+    v = r16(torch.randn(b, lk, h, d, device=DEV))
+    q[..., 51:] = 0
+    k[..., 51:] = 0
+    v[..., 51:] = 0
+    scale = 51 ** -0.5
+    kv_len = None
+    bias = None
+    if masked:
+        kv_len = torch.randint(1, lk + 1, (b,), device=DEV, dtype=torch.int32)
+        mask = torch.arange(lk, device=DEV)[None, :] < kv_len[:, None]
+        bias = ((1 - mask.float()) * -10000.0)[:, None, None, :]
+    ref = F.scaled_dot_product_attention(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3),
+                                         attn_mask=bias, scale=scale).permute(0, 2, 1, 3)
+    out = ops.attention(q.to(DT), k.to(DT), v.to(DT), scale, kv_len=kv_len)
+    assert rel(out, ref) < 2e-3
+
+
+def test_softmax_rows():
+    torch.manual_seed(10)
+    x = torch.randn(300, 4096, device=DEV) * 20
+    y = ops.softmax_rows(x, 512 ** -0.5)
+    assert rel(y, torch.softmax(x * 512 ** -0.5, -1)) < 1e-3
+
+
+def test_small_ops():
+    torch.manual_seed(11)
+    b = 5
+    x = torch.randn(b, 8, 256, 16, device=DEV)
+    y = ops.nchw_to_nhwc(x)
+    assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(ops.nhwc_to_nchw(y), x)
+    t = torch.full((b,), 999.0, device=DEV)
+    w = torch.rand(b, device=DEV) * 5
+    gw = torch.randn(512, device=DEV)
+    tf, gf = ops.time_features(t, w, gw)
+    f = torch.exp(-math.log(10000) * torch.arange(128, device=DEV, dtype=torch.float32) / 128)
+    arg = t[:, None] * f[None]
+    assert torch.allclose(tf, torch.cat([arg.cos(), arg.sin()], 1), atol=2e-4)
+    garg = (w.double()[:, None] * gw.double()[None]) * 2 * math.pi
+    assert torch.allclose(gf, torch.cat([garg.cos(), garg.sin()], 1).float(), atol=1e-5)
+    xw = torch.randn(b, 1024, device=DEV)
+    wt = torch.randn(300, 1024, device=DEV) / 32
+    bs = torch.randn(300, device=DEV)
+    out = ops.small_linear(xw, wt, bs, act_in=ops.ACT_SILU, act_out=ops.ACT_SILU)
+    assert rel(out, F.silu(F.silu(xw) @ wt.t() + bs)) < 1e-5
+    wav = torch.randn(3, 163872, device=DEV) * 0.3 + 0.05
+    i16, mm = ops.wave_to_int16(wav)
+    c = (wav.max() + wav.min()) / 2
+    ref = ((wav - c).cpu().numpy() * 32768).astype("int16")
+    assert (i16.cpu().numpy() == ref).all()
+    z = torch.randn(4, 8, 256, 16, device=DEV)
+    assert torch.allclose(ops.cfg_mix(z, 3.0), (1 - 3.0) * z[:2] + 3.0 * z[2:], atol=1e-6)
