@@ -24,7 +24,8 @@ constexpr int kBlockK = 64;                         // 64 x 16-bit = one 128-byt
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
-constexpr int kSmemBudget = 232448 - 1024;  // 227 KiB minus alignment slack
+constexpr int kSmemMaxDynamic = 232448 - 1024;     // 227 KiB minus the static barriers
+constexpr int kSmemBudget = kSmemMaxDynamic - 1024;  // minus alignment slack
 
 struct GemmKParams {
   // tiling
@@ -614,7 +615,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   const int smem_bytes = p.n_stages * p.stage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    CTTA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CTTA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic));
     attr_set = true;
   }
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;

@@ -1,0 +1,41 @@
+"""Single-step ConsistencyTTA generation restated: scheduler prologue -> UNet -> VAE decode -> vocoder.
+
+Follows easy_inference/consistencytta.py:135-200 and models/audio_consistency_model.py:430-507, with the text
+encoder replaced by given embeddings (FLAN-T5 is outside the hot path).
+"""
+import numpy as np
+import torch
+
+from . import hifigan, unet, vae
+
+
+def heun_sigmas(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
+    """HeunDiscreteScheduler.__init__ + set_timesteps (scaled_linear), scheduling_heun_discrete.py:100-227.
+    Returns float64 sigma per training timestep."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+    alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+    return np.array(((1 - alphas_cumprod) / alphas_cumprod) ** 0.5)
+
+
+def heun_first_step(num_inference_steps=18, num_train_timesteps=1000):
+    """(timesteps[0], init_noise_sigma) after set_timesteps(18): (999.0, 14.6146...)."""
+    sig = heun_sigmas(num_train_timesteps)
+    timesteps = np.linspace(0, num_train_timesteps - 1, num_inference_steps, dtype=float)[::-1].copy()
+    sigmas = np.interp(timesteps, np.arange(0, len(sig)), sig).astype(np.float32)
+    return float(timesteps[0]), float(sigmas.max())
+
+
+def generate(unet_sd, vae_sd, scale_factor, noise, enc, enc_mask, guidance, guidance_post=1.0):
+    """Returns (latent [B,8,256,16], mel [B,1,1024,64], float waveform [B,163872])."""
+    t0, sigma = heun_first_step()
+    z = noise * sigma  # consistencytta.py:160
+    use_cf = guidance_post > 1.0
+    z_in = torch.cat([z] * 2) if use_cf else z
+    z_in = z_in / ((sigma ** 2 + 1) ** 0.5)  # scale_model_input, scheduling_heun_discrete.py:151-172
+    out = unet.unet_forward(unet_sd, z_in, torch.tensor(t0, dtype=torch.float64), guidance, enc, enc_mask)
+    if use_cf:
+        u, c = out.chunk(2)
+        out = (1 - guidance_post) * u + guidance_post * c
+    mel = vae.decode_first_stage(vae_sd, out.float(), scale_factor)
+    wav = hifigan.decode_to_waveform(vae_sd, mel, return_float=True)
+    return out, mel, wav
