@@ -294,22 +294,25 @@ def im2col_s2(x):
     return out
 
 
-def nchw_to_nhwc(x, dtype=torch.float32, scale=1.0, c_pad=None):
-    """fp32 NCHW -> channels-last [N, H, W, c_pad] (zero padded channels)."""
+def nchw_to_nhwc(x, dtype=torch.float32, scale=1.0, c_pad=None, out=None):
+    """fp32 NCHW -> channels-last [N, H, W, c_pad] (zero padded channels), multiplied by `scale`."""
     _require_cuda(x)
     x = x.contiguous().float()
     n, c, h, w = x.shape
     cp = c_pad or c
-    out = (torch.zeros if cp != c else torch.empty)(n, h, w, cp, device=x.device, dtype=dtype)
+    if out is None:
+        out = (torch.zeros if cp != c else torch.empty)(n, h, w, cp, device=x.device, dtype=dtype)
+    dtype = out.dtype
     check(lib().ctta_nchw_to_nhwc(_ptr(x), n, c, h * w, _ptr(out), _DT[dtype], cp, scale, _stream()))
     return out
 
 
-def nhwc_to_nchw(x, c=None):
+def nhwc_to_nchw(x, c=None, out=None):
     """fp32 channels-last [N, H, W, ld] -> fp32 NCHW [N, c, H, W]."""
     n, h, w, ld = x.shape
     c = c or ld
-    out = torch.empty(n, c, h, w, device=x.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(n, c, h, w, device=x.device, dtype=torch.float32)
     check(lib().ctta_nhwc_to_nchw(_ptr(x), n, c, h * w, x.stride(2), _ptr(out), _stream()))
     return out
 
@@ -332,20 +335,22 @@ def small_linear(x, weight, bias, act_in=ACT_NONE, act_out=ACT_NONE, accumulate=
     return out
 
 
-def wave_to_int16(wav, minmax=None):
+def wave_to_int16(wav, minmax=None, out=None):
     """Batch-global centring + int16 truncation (hifigan/utilities.py:84-86). Returns (int16 tensor, minmax)."""
     numel = wav.numel()
     if minmax is None:
         minmax = torch.empty(2, device=wav.device, dtype=torch.float32)
         check(lib().ctta_wave_minmax(_ptr(wav), numel, _ptr(minmax), _stream()))
-    out = torch.empty(wav.shape, device=wav.device, dtype=torch.int16)
+    if out is None:
+        out = torch.empty(wav.shape, device=wav.device, dtype=torch.int16)
     check(lib().ctta_wave_to_int16(_ptr(wav), numel, _ptr(minmax), _ptr(out), _stream()))
     return out, minmax
 
 
-def cfg_mix(x, s):
+def cfg_mix(x, s, out=None):
     half = x.shape[0] // 2
-    out = torch.empty((half,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((half,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
     check(lib().ctta_cfg_mix(_ptr(x), out.numel(), s, _ptr(out), _stream()))
     return out
 

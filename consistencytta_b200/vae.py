@@ -1,0 +1,316 @@
+"""Drop-in AutoencoderKL (decode side) + HiFi-GAN Generator running on libctta kernels.
+
+Mirrors audioldm/variational_autoencoder/autoencoder.py:9-111 (AutoencoderKL: decode_first_stage,
+decode_to_waveform, .decoder/.post_quant_conv/.vocoder/.scale_factor), modules.py:546-683 (Decoder) and
+audioldm/hifigan/models.py:66-117 (Generator) with the reference's state_dict keys.  The encode side
+(encoder.*, quant_conv.*) is training/eval only and out of scope: its keys are accepted and ignored.
+"""
+import torch
+from torch import nn
+
+from . import ops, weights
+from .module_base import PackedModule, _Node, register_tree
+from .ops import ACT_LRELU, ACT_NONE, ACT_SILU, ACT_TANH
+
+GROUPS = 32
+EPS = 1e-6  # Normalize(), modules.py:38-41
+
+
+class Generator(PackedModule):
+    """HiFi-GAN V1 generator, HIFIGAN_16K_64 (hifigan/utilities.py:9-39). forward(mel [B, 64, T]) -> [B, 1, T*160+32]."""
+
+    def __init__(self, h=None):
+        super().__init__()
+        self.h = dict(weights.HIFIGAN_CONFIG)
+        if h is not None:
+            self.h.update({k: h[k] for k in weights.HIFIGAN_CONFIG if k in h})
+        self.num_kernels = len(self.h["resblock_kernel_sizes"])
+        self.num_upsamples = len(self.h["upsample_rates"])
+        register_tree(self, weights.vocoder_schema(self.h, prefix=""))
+
+    def remove_weight_norm(self):
+        """Weights are stored folded (hifigan/utilities.py:71); nothing to do."""
+
+    def _pack(self, sd, dev):
+        pk = {}
+        sd = {k: v.to(dev) for k, v in sd.items()}
+        pk["conv_pre"] = ops.pack_conv1d(sd["conv_pre.weight"], sd["conv_pre.bias"])
+        for i, (u, k) in enumerate(zip(self.h["upsample_rates"], self.h["upsample_kernel_sizes"])):
+            pk["ups.%d" % i] = ops.pack_conv_transpose1d(sd["ups.%d.weight" % i], sd["ups.%d.bias" % i], u, (k - u) // 2)
+            for j, (ks, dils) in enumerate(zip(self.h["resblock_kernel_sizes"], self.h["resblock_dilation_sizes"])):
+                n = i * self.num_kernels + j
+                for m, d in enumerate(dils):
+                    pk["rb.%d.c1.%d" % (n, m)] = ops.pack_conv1d(sd["resblocks.%d.convs1.%d.weight" % (n, m)],
+                                                                 sd["resblocks.%d.convs1.%d.bias" % (n, m)], dilation=d)
+                    pk["rb.%d.c2.%d" % (n, m)] = ops.pack_conv1d(sd["resblocks.%d.convs2.%d.weight" % (n, m)],
+                                                                 sd["resblocks.%d.convs2.%d.bias" % (n, m)], dilation=1)
+        pk["conv_post"] = ops.pack_conv1d(sd["conv_post.weight"], sd["conv_post.bias"])
+        return pk
+
+    def out_length(self, t):
+        for u, k in zip(self.h["upsample_rates"], self.h["upsample_kernel_sizes"]):
+            t = (t - 1) * u - 2 * ((k - u) // 2) + k
+        return t
+
+    def forward_btc(self, mel16):
+        """mel16: 16-bit channels-last [B, T, 64] -> fp32 waveform [B, T_out].
+
+        Every LeakyReLU / residual add / MRF sum / divide-by-3 / tanh of models.py:56-63,101-117 is a GEMM epilogue:
+        convs emit the fp32 residual stream plus the LeakyReLU'ed 16-bit operand of the next conv."""
+        pk = self.packed()
+        dev = mel16.device
+        f16 = ops.OPERAND_DTYPE
+        b, t, _ = mel16.shape
+        c = self.h["upsample_initial_channel"]
+        cur16 = torch.empty(b, t, c, device=dev, dtype=f16)
+        ops.conv1d(mel16, pk["conv_pre"], out2=cur16, act2=ACT_LRELU, act2_slope=0.1)  # models.py:102,104
+        nk = self.num_kernels
+        for i, (u, k) in enumerate(zip(self.h["upsample_rates"], self.h["upsample_kernel_sizes"])):
+            c //= 2
+            t = (t - 1) * u - 2 * ((k - u) // 2) + k
+            x = torch.empty(b, t, c, device=dev, dtype=torch.float32)
+            x16 = torch.empty(b, t, c, device=dev, dtype=f16)
+            ops.conv_transpose1d(cur16, pk["ups.%d" % i], t, out=x, out2=x16, act2=ACT_LRELU, act2_slope=0.1)
+            xs = torch.empty(b, t, c, device=dev, dtype=torch.float32)
+            nxt16 = torch.empty(b, t, c, device=dev, dtype=f16)
+            tmp16 = torch.empty(b, t, c, device=dev, dtype=f16)
+            r_a = torch.empty(b, t, c, device=dev, dtype=torch.float32)
+            r_b = torch.empty(b, t, c, device=dev, dtype=torch.float32)
+            r16 = torch.empty(b, t, c, device=dev, dtype=f16)
+            last = i == self.num_upsamples - 1
+            for j in range(nk):
+                n = i * nk + j
+                res, a16 = x, x16
+                for m in range(3):
+                    ops.conv1d(a16, pk["rb.%d.c1.%d" % (n, m)], out2=tmp16, act2=ACT_LRELU, act2_slope=0.1)
+                    if m < 2:
+                        dst = r_a if m == 0 else r_b
+                        ops.conv1d(tmp16, pk["rb.%d.c2.%d" % (n, m)], out=dst, residual=res, out2=r16,
+                                   act2=ACT_LRELU, act2_slope=0.1)
+                        res, a16 = dst, r16
+                    else:
+                        fin = j == nk - 1
+                        ops.conv1d(tmp16, pk["rb.%d.c2.%d" % (n, m)], out=xs, residual=res, accumulate=j > 0,
+                                   out_scale=(1.0 / nk) if fin else 1.0, out2=nxt16 if fin else None,
+                                   act2=ACT_LRELU, act2_slope=0.01 if last else 0.1)
+            cur16 = nxt16
+        wav = torch.empty(b, t, 1, device=dev, dtype=torch.float32)
+        ops.conv1d(cur16, pk["conv_post"], out=wav, act=ACT_TANH)  # models.py:113-115
+        return wav.view(b, t)
+
+    def forward(self, x):
+        """Reference signature: x [B, num_mels, T] fp32 -> [B, 1, T_out]."""
+        mel16 = x.transpose(1, 2).contiguous().to(ops.OPERAND_DTYPE)
+        return self.forward_btc(mel16).unsqueeze(1)
+
+
+class Decoder(PackedModule):
+    """LDM-style conv decoder 8x256x16 -> 1x1024x64, modules.py:546-683."""
+
+    def __init__(self, **ddconfig):
+        super().__init__()
+        cfg = {"embed_dim": weights.VAE_CONFIG["embed_dim"], "ddconfig": dict(weights.VAE_CONFIG["ddconfig"])}
+        cfg["ddconfig"].update({k: v for k, v in ddconfig.items() if k in cfg["ddconfig"]})
+        if cfg["ddconfig"] != weights.VAE_CONFIG["ddconfig"]:
+            raise ValueError("only the audioldm-s-full first-stage decoder is implemented")
+        sch = {k[len("decoder."):]: v for k, v in weights.vae_decoder_schema(cfg).items() if k.startswith("decoder.")}
+        register_tree(self, sch)
+
+    def _pack(self, sd, dev):
+        pk = {}
+        sd = {k: v.to(dev) for k, v in sd.items()}
+        for k in sd:
+            if k.endswith(".weight"):
+                name = k[:-7]
+                w = sd[k]
+                if w.dim() == 4:
+                    pk[name] = ops.pack_conv2d(w, sd[name + ".bias"])
+                else:
+                    pk[name] = (w.float().contiguous(), sd[name + ".bias"].float().contiguous())
+        return pk
+
+    def _resnet(self, pk, p, x):
+        """ResnetBlock.forward (temb None), modules.py:155-175."""
+        b, h, w, cin = x.shape
+        dev = x.device
+        has_sc = (p + ".nin_shortcut") in pk
+        st = ops.groupnorm_stats(x, GROUPS)
+        raw = torch.empty(b, h, w, cin, device=dev, dtype=ops.OPERAND_DTYPE) if has_sc else None
+        a = ops.groupnorm_apply(x, GROUPS, st, *pk[p + ".norm1"], eps=EPS, act=ACT_SILU, raw_out=raw)
+        cout = pk[p + ".conv1"].n
+        hid = torch.empty(b, h, w, cout, device=dev, dtype=torch.float32)
+        ops.conv2d(a, pk[p + ".conv1"], out=hid)
+        del a
+        st2 = ops.groupnorm_stats(hid, GROUPS)
+        a2 = ops.groupnorm_apply(hid, GROUPS, st2, *pk[p + ".norm2"], eps=EPS, act=ACT_SILU)
+        if has_sc:
+            res = torch.empty(b, h, w, cout, device=dev, dtype=torch.float32)
+            ops.conv2d(raw, pk[p + ".nin_shortcut"], out=res)
+        else:
+            res = x
+        ops.conv2d(a2, pk[p + ".conv2"], out=hid, residual=res)
+        return hid
+
+    def _attn(self, pk, p, x):
+        """AttnBlock.forward, modules.py:204-230: single head over H*W tokens, d = C = 512.
+        scores and P.V run on the tcgen05 GEMM per sample; V's bias is added after P.V (softmax rows sum to 1)."""
+        b, h, w, c = x.shape
+        dev = x.device
+        f16 = ops.OPERAND_DTYPE
+        n = h * w
+        st = ops.groupnorm_stats(x, GROUPS)
+        a = ops.groupnorm_apply(x, GROUPS, st, *pk[p + ".norm"], eps=EPS, act=ACT_NONE).view(b, n, c)
+        q = torch.empty(b, n, c, device=dev, dtype=f16)
+        k = torch.empty(b, n, c, device=dev, dtype=f16)
+        ops.linear(a.view(b * n, c), pk[p + ".q"], out=q.view(b * n, c))
+        ops.linear(a.view(b * n, c), pk[p + ".k"], out=k.view(b * n, c))
+        wv = pk[p + ".v"]
+        o = torch.empty(b, n, c, device=dev, dtype=f16)
+        s = torch.empty(n, n, device=dev, dtype=torch.float32)
+        pr = torch.empty(n, n, device=dev, dtype=f16)
+        vt = torch.empty(c, n, device=dev, dtype=f16)
+        for i in range(b):
+            # V^T[c, token] = W_v[c, :] . a[token, :]  (a as the K-major "weight" operand)
+            ops.linear(wv.w, ops.PackedWeight(a[i], None, 1, c, n, [0], [0]), out=vt)
+            ops.linear(q[i], ops.PackedWeight(k[i], None, 1, c, n, [0], [0]), out=s)
+            ops.softmax_rows(s, float(c) ** -0.5, out=pr)
+            ops.linear(pr, ops.PackedWeight(vt, wv.bias, 1, n, c, [0], [0]), out=o[i])
+        out = torch.empty(b, h, w, c, device=dev, dtype=torch.float32)
+        ops.linear(o.view(b * n, c), pk[p + ".proj_out"], out=out.view(b * n, c), residual=x.view(b * n, c))
+        return out
+
+    def forward_nhwc(self, z16, out16=None):
+        """z16: 16-bit channels-last [B, 256, 16, 8] (after post_quant_conv) -> fp32 [B, 1024, 64, 1]."""
+        pk = self.packed()
+        dev = z16.device
+        b, h, w, _ = z16.shape
+        x = torch.empty(b, h, w, pk["conv_in"].n, device=dev, dtype=torch.float32)
+        ops.conv2d(z16, pk["conv_in"], out=x)
+        x = self._resnet(pk, "mid.block_1", x)
+        x = self._attn(pk, "mid.attn_1", x)
+        x = self._resnet(pk, "mid.block_2", x)
+        for lvl in (2, 1, 0):
+            for blk in range(3):
+                x = self._resnet(pk, "up.%d.block.%d" % (lvl, blk), x)
+            if lvl != 0:  # Upsample, modules.py:53-57
+                bb, hh, ww, cc = x.shape
+                up = ops.groupnorm_apply(x, 1, None, None, None, act=ACT_NONE, upsample=True)
+                del x
+                x = torch.empty(bb, 2 * hh, 2 * ww, cc, device=dev, dtype=torch.float32)
+                ops.conv2d(up, pk["up.%d.upsample.conv" % lvl], out=x)
+                del up
+        st = ops.groupnorm_stats(x, GROUPS)
+        a = ops.groupnorm_apply(x, GROUPS, st, *pk["norm_out"], eps=EPS, act=ACT_SILU)
+        bb, hh, ww, _ = x.shape
+        del x
+        out = torch.empty(bb, hh, ww, 1, device=dev, dtype=torch.float32)
+        ops.conv2d(a, pk["conv_out"], out=out, out2=out16)
+        return out
+
+    def forward(self, z):
+        """Reference signature: z fp32 NCHW [B, 8, 256, 16] -> [B, 1, 1024, 64]."""
+        z16 = ops.nchw_to_nhwc(z.float(), dtype=ops.OPERAND_DTYPE)
+        out = self.forward_nhwc(z16)
+        b, h, w, _ = out.shape
+        return out.view(b, 1, h, w)
+
+
+class AutoencoderKL(nn.Module):
+    """autoencoder.py:9-111, decode side."""
+
+    def __init__(self, ddconfig=None, lossconfig=None, image_key="fbank", embed_dim=None, time_shuffle=1, subband=1,
+                 ckpt_path=None, reload_from_ckpt=None, ignore_keys=(), colorize_nlabels=None, monitor=None,
+                 base_learning_rate=1e-5, scale_factor=1):
+        super().__init__()
+        ddconfig = ddconfig or weights.VAE_CONFIG["ddconfig"]
+        embed_dim = embed_dim or weights.VAE_CONFIG["embed_dim"]
+        self.decoder = Decoder(**ddconfig)
+        self.ema_decoder = None
+        self.subband = int(subband)
+        if self.subband != 1:
+            raise NotImplementedError("subband decomposition is not used by ConsistencyTTA")
+        self.post_quant_conv = _Node()
+        z = ddconfig["z_channels"]
+        self.post_quant_conv.register_parameter("weight", nn.Parameter(torch.zeros(z, embed_dim, 1, 1), False))
+        self.post_quant_conv.register_parameter("bias", nn.Parameter(torch.zeros(z), False))
+        self.ema_post_quant_conv = None
+        self.vocoder = Generator()
+        self.embed_dim = embed_dim
+        self.image_key = image_key
+        self.time_shuffle = time_shuffle
+        self.scale_factor = scale_factor
+        self._pq = None
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts the reference's 398-key VAE state_dict; encode-side tensors are dropped (out of scope)."""
+        sd = {k: v for k, v in state_dict.items() if not k.startswith(("encoder.", "quant_conv."))}
+        self._pq = None
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    def _apply(self, fn, *a, **k):
+        self._pq = None
+        return super()._apply(fn, *a, **k)
+
+    def encode(self, x):
+        raise NotImplementedError("the VAE encode side is training/evaluation only (SURVEY.md 8a V1)")
+
+    encode_first_stage = encode
+
+    def _post_quant(self, use_ema, z_scale):
+        """post_quant_conv 1x1 (autoencoder.py:99) with `z / scale_factor` (:105) folded into its weights."""
+        mod = self.post_quant_conv
+        if use_ema and self.ema_post_quant_conv is not None:
+            mod = self.ema_post_quant_conv
+        key = (id(mod), float(z_scale))
+        if self._pq is None or self._pq[0] != key:
+            self._pq = (key, ops.pack_conv2d(mod.weight.detach().float() * float(z_scale), mod.bias.detach()))
+        return self._pq[1]
+
+    def decode_nhwc(self, z_nhwc, use_ema=False, z_scale=1.0, mel16=None):
+        """z_nhwc: fp32 channels-last latent [B, 256, 16, 8] -> fp32 [B, 1024, 64, 1] (== NCHW [B,1,1024,64]).
+        Computes Decoder(post_quant_conv(z * z_scale)); mel16 (optional, [B,1024,64,1] 16-bit) gets a 16-bit copy."""
+        if use_ema and self.ema_decoder is None:
+            print("VAE does not have EMA modules, but specified use_ema. Using the none-EMA modules instead.")
+        dec = self.ema_decoder if (use_ema and self.ema_decoder is not None) else self.decoder
+        b, h, w, c = z_nhwc.shape
+        z16 = ops.groupnorm_apply(z_nhwc, 1, None, None, None, act=ACT_NONE)
+        zq = torch.empty(b, h, w, c, device=z_nhwc.device, dtype=ops.OPERAND_DTYPE)
+        ops.conv2d(z16, self._post_quant(use_ema, z_scale), out=zq)
+        return dec.forward_nhwc(zq, out16=mel16)
+
+    def decode(self, z, use_ema=False):
+        zn = ops.nchw_to_nhwc(z.float(), dtype=torch.float32)
+        out = self.decode_nhwc(zn, use_ema)
+        b, h, w, _ = out.shape
+        return out.view(b, 1, h, w)
+
+    def decode_first_stage(self, z, allow_grad=False, use_ema=False):
+        """autoencoder.py:103-106."""
+        if allow_grad:
+            raise NotImplementedError("allow_grad=True (training losses) is out of scope (SURVEY.md 8f N4)")
+        with torch.no_grad():
+            zn = ops.nchw_to_nhwc(z.float(), dtype=torch.float32)
+            out = self.decode_nhwc(zn, use_ema, z_scale=1.0 / float(self.scale_factor))
+            b, h, w, _ = out.shape
+            return out.view(b, 1, h, w)
+
+    def waveform_from_mel_nhwc(self, mel16):
+        """mel16 16-bit [B, T, 64] -> (int16 [B, T_out] tensor on device, fp32 waveform)."""
+        wav = self.vocoder.forward_btc(mel16)
+        i16, _ = ops.wave_to_int16(wav)
+        return i16, wav
+
+    def decode_to_waveform(self, dec, allow_grad=False):
+        """autoencoder.py:108-111 + vocoder_infer (hifigan/utilities.py:76-91) -> numpy int16 [B, 163872]."""
+        if allow_grad:
+            raise NotImplementedError("allow_grad=True (training losses) is out of scope (SURVEY.md 8f N4)")
+        with torch.no_grad():
+            b, _, t, m = dec.shape
+            # [B,1,T,mel].squeeze(1).permute(0,2,1) is [B,mel,T]; channels-last [B,T,mel] is dec's own memory layout
+            mel16 = ops.groupnorm_apply(dec.float().contiguous().view(b, t, 1, m), 1, None, None, None, act=ACT_NONE)
+            i16, _ = self.waveform_from_mel_nhwc(mel16.view(b, t, m))
+            return i16.cpu().numpy()

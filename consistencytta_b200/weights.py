@@ -250,3 +250,16 @@ def make_vae_state_dict(seed=1):
 
 
 SCALE_FACTOR = 0.9227  # arbitrary fixed latent scale (the real value lives in the AudioLDM checkpoint)
+
+
+def synthetic_inputs(batch, length, seed=1234):
+    """Deterministic synthetic inputs shared by the golden script, the tests and bench.py:
+    noise [B,8,256,16] ~ N(0,1), text embeddings [B,L,1024] ~ N(0,1), bool mask with ragged trailing padding."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    noise = torch.randn(batch, 8, 256, 16, generator=g)
+    enc = torch.randn(batch, length, 1024, generator=g)
+    mask = torch.ones(batch, length, dtype=torch.bool)
+    for b in range(1, batch):
+        mask[b, length - min(length - 1, (4 * b + 8) % length):] = False  # trailing padding, different per row
+    return noise, enc, mask

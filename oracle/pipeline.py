@@ -14,7 +14,7 @@ def heun_sigmas(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
     Returns float64 sigma per training timestep."""
     betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
     alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
-    return np.array(((1 - alphas_cumprod) / alphas_cumprod) ** 0.5)
+    return (((1 - alphas_cumprod) / alphas_cumprod) ** 0.5).numpy()
 
 
 def heun_first_step(num_inference_steps=18, num_train_timesteps=1000):

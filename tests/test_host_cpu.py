@@ -1,0 +1,114 @@
+"""CPU-side tests: oracle against the golden vectors of the reference, schemas, scheduler, and the C-ABI surface."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def test_schema_matches_reference_state_dicts():
+    from consistencytta_b200 import weights
+    ref = json.load(open(os.path.join(GOLD, "state_dict_schema.json")))
+    ours = {k: list(s) for k, (s, _) in weights.unet_schema().items()}
+    assert ours == ref["unet"] and len(ours) == 691
+    assert sum(int(np.prod(s)) for s in ours.values()) == 559209676
+    vae = {k: list(s) for k, (s, _) in weights.vae_schema().items()}
+    ref_dec = {k: v for k, v in ref["vae"].items() if not k.startswith(("encoder.", "quant_conv."))}
+    assert vae == ref_dec
+    assert len([k for k in vae if k.startswith("vocoder.")]) == 194 and len(ref["vae"]) == 398
+
+
+def test_synthetic_weights_deterministic():
+    from consistencytta_b200 import weights
+    a = weights.make_state_dict(weights.vocoder_schema(), 1)
+    b = weights.make_state_dict(weights.vocoder_schema(), 1)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert abs(a["vocoder.resblocks.0.convs1.0.weight"].std().item() - 0.01) < 1e-3
+
+
+def test_scheduler_matches_reference_constants():
+    from consistencytta_b200 import HeunDiscreteScheduler
+    from oracle import pipeline as op
+    s = HeunDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-2-1", subfolder="scheduler")
+    s.set_timesteps(18)
+    rep = json.load(open(os.path.join(GOLD, "reference_report.json")))
+    assert float(s.timesteps[0]) == rep["t0"] == 999.0
+    assert abs(float(s.init_noise_sigma) - rep["sigma_max"]) < 1e-6
+    assert len(s.timesteps) == 35 and len(s.sigmas) == 36
+    t0, sig = op.heun_first_step()
+    assert t0 == 999.0 and abs(sig - rep["sigma_max"]) < 1e-6
+    x = torch.ones(2, 8, 4, 4)
+    assert torch.allclose(s.scale_model_input(x, s.timesteps[0]), x / (sig ** 2 + 1) ** 0.5)
+
+
+def test_oracle_vocoder_matches_reference_golden():
+    """Cheap oracle leg (the UNet / VAE legs take seconds each and are covered by test_oracle_full_chain)."""
+    from consistencytta_b200 import weights
+    from oracle import hifigan
+    gold = torch.load(os.path.join(GOLD, "reference_outputs.pt"))
+    sd = weights.make_state_dict(weights.vocoder_schema(), 1)
+    wav = hifigan.decode_to_waveform(sd, gold["c_mel"], return_float=True)
+    assert rel(wav, gold["c_wav"]) < 1e-5
+
+
+def test_oracle_full_chain_matches_reference_golden():
+    from consistencytta_b200 import weights
+    from oracle import hifigan, pipeline
+    gold = torch.load(os.path.join(GOLD, "reference_outputs.pt"))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    noise, enc, mask = weights.synthetic_inputs(1, 32)
+    with torch.no_grad():
+        lat, mel, wav = pipeline.generate(weights.make_unet_state_dict(0), weights.make_vae_state_dict(1),
+                                          weights.SCALE_FACTOR, noise, enc, mask, 4.0)
+    assert lat.shape == (1, 8, 256, 16) and mel.shape == (1, 1, 1024, 64) and wav.shape == (1, 163872)
+    assert rel(lat, gold["a_latent"]) < 1e-4 and rel(mel, gold["a_mel"]) < 1e-4 and rel(wav, gold["a_wav"]) < 1e-4
+    i16 = hifigan.to_int16(wav)
+    assert np.abs(i16.astype(np.int32) - gold["a_wav_i16"].numpy().astype(np.int32)).max() <= 1
+
+
+def test_numpy_int16_semantics():
+    """hifigan/utilities.py:86 relies on numpy's float->int16 cast: truncation toward zero, wrap on overflow."""
+    x = np.array([0.9, -1.7, 40000.7, -40000.7, 32767.9], dtype=np.float32)
+    assert x.astype("int16").tolist() == [0, -1, -25536, 25536, 32767]
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from consistencytta_b200 import _lib, build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "ctta.h")).read()
+    declared = set(re.findall(r"\b(ctta_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), "missing export %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib.ctta_version.restype = ctypes.c_int
+    assert lib.ctta_version() >= 100
+    # struct mirror must match the C layout
+    assert ctypes.sizeof(_lib.GemmDesc) % 8 == 0
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "consistencytta_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_modules_refuse_cpu():
+    from consistencytta_b200 import UNet2DConditionGuidedModel
+    u = UNet2DConditionGuidedModel()
+    assert len(u.state_dict()) == 691
+    with pytest.raises(RuntimeError):
+        u(torch.zeros(1, 8, 256, 16), 999.0, guidance=4.0, encoder_hidden_states=torch.zeros(1, 4, 1024))
