@@ -1,7 +1,9 @@
 // Implicit-GEMM convolution / linear kernel for sm_100a.
 //
-//   * one persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer + TMEM owner,
-//     warps 2..5 = epilogue (TMEM -> registers -> global, one accumulator row per thread)
+//   * one persistent CTA per SM, 7 warps: warp 0 = TMA producer (A/W tiles), warp 1 = tcgen05.mma issuer + TMEM
+//     owner, warp 2 = epilogue loader (TMA-prefetches residual / accumulate tiles into a shared-memory ring so
+//     their latency hides behind the mainloop), warps 3..6 = epilogue math (TMEM -> registers -> swizzled shared
+//     memory -> TMA store: every global access of the epilogue is a full-line bulk transfer)
 //   * A (activations, channels-last) is never im2col'ed: for filter tap j the producer issues a tiled TMA load
 //     of the 128-pixel box shifted by (dh_j, dw_j); TMA's out-of-bounds zero fill IS the conv zero padding.
 //     The landed box is 128 rows x 64 channels x 16 bit = rows of 128 B with the 128-byte swizzle, i.e. the
@@ -14,6 +16,7 @@
 //
 // Reference call sites replaced: see ctta_gemm in include/ctta.h.
 #include <cuda.h>
+#include <cstring>
 #include "ctta_internal.h"
 #include "ctta_ptx.cuh"
 
@@ -23,9 +26,15 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                         // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;
 constexpr int kSmemMaxDynamic = 232448 - 1024;     // 227 KiB minus the static barriers
 constexpr int kSmemBudget = kSmemMaxDynamic - 1024;  // minus alignment slack
+constexpr int kEpiWarp0 = 3;                         // first of the 4 epilogue math warps
+constexpr int kChunkCols = 32;                       // accumulator columns per epilogue chunk
+constexpr int kRingSlotBytes = kBlockM * kChunkCols * 4;  // 16 KiB: 128 rows x 32 fp32 columns (128-B swizzle)
+constexpr int kMaxRing = 6;
+constexpr int kStage16Bytes = 32 * kChunkCols * 2;   // 2 KiB: 32 rows x 32 16-bit columns per warp per buffer
+constexpr int kBiasBytes = 2 * 256 * 4;
 
 struct GemmKParams {
   // tiling
@@ -56,6 +65,14 @@ struct GemmKParams {
   float act2_slope;
   int out_rows_per_img, out_stride, out_off;
   int vec_ok;  // all pointers 16-B aligned and all lds multiples of 8 -> 8-column vector path allowed
+  // TMA-staged epilogue
+  int epi_tma;             // 1: outputs / residual go through shared memory + TMA; 0: direct per-thread global access
+  int ring_slots;          // number of 16-KiB fp32 ring slots (0 when the ring is unused)
+  int ring_in;             // fp32 input tiles per chunk loaded by the loader warp (residual, previous out): 0..2
+  int ring_per_chunk;      // ring slots consumed per chunk (max(ring_in, 1) when the ring is used)
+  int out_rows_tile_img;   // rows of one image inside a 128-row tile (128 / box_n)
+  int row_coord_shift;     // logical row -> TMA row coordinate (transposed-conv phases start at q_start)
+  int ring_off, stage16_off, bias_off;  // byte offsets from the 1024-aligned dynamic smem base
 };
 
 struct TileCoord {
@@ -265,12 +282,15 @@ __device__ __forceinline__ void epilogue8(const GemmKParams& p, float* v, int co
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ GemmKParams p) {
+               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
+               const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kMaxStages];
   __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
   __shared__ __align__(8) uint64_t bar_tmem_full[2];
   __shared__ __align__(8) uint64_t bar_tmem_empty[2];
+  __shared__ __align__(8) uint64_t bar_ring_full[kMaxRing];
+  __shared__ __align__(8) uint64_t bar_ring_empty[kMaxRing];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -286,9 +306,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(smem_u32(&bar_tmem_full[s]), 1);
       mbar_init(smem_u32(&bar_tmem_empty[s]), 4);  // one arrive per epilogue warp
     }
+    for (int s = 0; s < kMaxRing; ++s) {
+      mbar_init(smem_u32(&bar_ring_full[s]), 1);
+      mbar_init(smem_u32(&bar_ring_empty[s]), 4);
+    }
     mbar_fence_init();
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.epi_tma) {
+      if (p.out) tma_prefetch_desc(&tmap_out);
+      if (p.out2) tma_prefetch_desc(&tmap_out2);
+      if (p.residual) tma_prefetch_desc(&tmap_res);
+    }
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(&tmem_base_slot), static_cast<uint32_t>(p.tmem_cols));
@@ -367,8 +396,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         umma_commit(smem_u32(&bar_tmem_full[acc]));  // accumulator complete -> epilogue
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue warps
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ epilogue loader (one lane)
+    // Streams the fp32 residual / previous-output tiles of every chunk into the ring, running ahead of the
+    // epilogue math by up to ring_slots chunks.  With no inputs it only hands out free slots (pure staging).
+    if (lane == 0 && p.epi_tma && p.ring_slots > 0) {
+      const int n_chunks = p.block_n / kChunkCols;
+      const uint32_t ring_base = tiles_base + static_cast<uint32_t>(p.ring_off);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        int row0, img0;
+        if (p.a_mode == CTTA_A_ROWS) {
+          row0 = tc.c1; img0 = 0;
+        } else if (p.a_mode == CTTA_A_CONV1D) {
+          row0 = tc.c1; img0 = tc.c2;
+        } else {
+          row0 = tc.c2 * p.W + tc.c1; img0 = tc.c3;
+        }
+        row0 -= p.row_coord_shift;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          const int col = tc.n0 + ch * kChunkCols;
+          for (int k = 0; k < p.ring_per_chunk; ++k) {
+            mbar_wait(smem_u32(&bar_ring_empty[slot]), phase ^ 1u);
+            const uint32_t full = smem_u32(&bar_ring_full[slot]);
+            if (k < p.ring_in) {
+              mbar_arrive_expect_tx(full, kRingSlotBytes);
+              // input 0 = residual (if any), then the previous contents of out (accumulate);
+              // one {32 cols x 32 rows} box per epilogue warp (the same box shape the stores use)
+              const bool is_res = (k == 0 && p.residual != nullptr);
+              const void* map = is_res ? static_cast<const void*>(&tmap_res) : static_cast<const void*>(&tmap_out);
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) {
+                const int wr = qq * 32;
+                tma_load_3d(ring_base + slot * kRingSlotBytes + wr * 128, map, full, col,
+                            row0 + (wr % p.out_rows_tile_img), img0 + wr / p.out_rows_tile_img);
+              }
+            } else {
+              mbar_arrive(full);
+            }
+            if (++slot == p.ring_slots) {
+              slot = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (!p.epi_tma) {
+    // ------------------------------------------------------------------ epilogue warps, direct global access
+    // (tiny / unaligned outputs: N <= 16 or row pitch not a multiple of 16 bytes)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int lr = q * 32 + lane;
     int it = 0;
@@ -433,6 +511,202 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps, TMA-staged
+    // thread = accumulator row.  Per 32-column chunk: TMEM -> registers, + bias (smem broadcast) + rowadd, act,
+    // + residual / previous out (ring slot, prefetched by warp 2), scale; fp32 result written back in place into
+    // the ring slot, 16-bit results into the per-warp staging buffer; one lane issues the TMA stores.
+    const int q = warp & 3;
+    const int ew = warp - kEpiWarp0;          // 0..3, owner of staging buffers
+    const int lr = q * 32 + lane;             // row inside the tile
+    const int n_chunks = p.block_n / kChunkCols;
+    const uint32_t ring_base = tiles_base + static_cast<uint32_t>(p.ring_off);
+    const uint32_t st16_base = tiles_base + static_cast<uint32_t>(p.stage16_off) + ew * 2 * kStage16Bytes;
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (tiles_base - smem_u32(smem_raw)) + p.bias_off);
+    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
+    const bool out_f32 = p.out != nullptr && p.out_dtype == CTTA_F32;
+    const bool out_16 = p.out != nullptr && p.out_dtype != CTTA_F32;
+    const bool geglu = p.act == CTTA_ACT_GEGLU;
+    const int sw7 = lane & 7;
+    int slot = 0;
+    uint32_t ring_phase = 0;
+    int pending_slot = -1;  // ring slot whose TMA store may still be reading shared memory
+    uint32_t chunk_ctr = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const TileCoord tc = decode_tile(p, tile);
+      int row0, img0;
+      if (p.a_mode == CTTA_A_ROWS) {
+        row0 = tc.c1; img0 = 0;
+      } else if (p.a_mode == CTTA_A_CONV1D) {
+        row0 = tc.c1; img0 = tc.c2;
+      } else {
+        row0 = tc.c2 * p.W + tc.c1; img0 = tc.c3;
+      }
+      // this warp's 32 rows: coordinates of the store box
+      const int wrow = q * 32;
+      const int st_row = row0 + (wrow % p.out_rows_tile_img) - p.row_coord_shift;
+      const int st_img = img0 + wrow / p.out_rows_tile_img;
+      long long ra_row = 0;
+      if (p.rowadd) {
+        const int r_in_img = (p.a_mode == CTTA_A_CONV2D) ? (row0 + (lr % p.out_rows_tile_img)) : (row0 + lr);
+        const int img = (p.a_mode == CTTA_A_CONV2D) ? (img0 + lr / p.out_rows_tile_img) : img0;
+        long long gr = static_cast<long long>(img) * p.rows_per_img + r_in_img;
+        const long long gmax = static_cast<long long>(p.n_img) * p.rows_per_img - 1;
+        if (gr > gmax) gr = gmax;  // rows past the end are clipped by the TMA store; keep the load in bounds
+        ra_row = gr / p.rowadd_rows;
+      }
+      // bias of this tile -> shared memory (double buffered by tile parity)
+      float* bs = bias_s + (it & 1) * 256;
+      for (int i = et; i < p.block_n; i += 128) {
+        const int c = tc.n0 + i;
+        bs[i] = (p.bias != nullptr && c < p.N) ? p.bias[c] : 0.f;
+      }
+      named_barrier_sync(1, 128);
+
+      mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
+      for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
+        const int c0 = ch * kChunkCols;
+        const int col = tc.n0 + c0;
+        uint32_t u[32];
+        tmem_ld_x32(t_addr + c0, u);
+        // per-row additive term (time embedding): issue the loads before waiting on TMEM / the ring
+        float4 ra[8];
+        if (p.rowadd) {
+          const float* rp = p.rowadd + ra_row * p.rowadd_ld + col;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (col + 4 * g + 3 < p.N) ra[g] = __ldg(reinterpret_cast<const float4*>(rp + 4 * g));
+            else ra[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        tmem_ld_wait();
+        if (ch == n_chunks - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+        }
+        float v[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bs + c0 + 4 * g);
+          v[4 * g + 0] = __uint_as_float(u[4 * g + 0]) + b4.x;
+          v[4 * g + 1] = __uint_as_float(u[4 * g + 1]) + b4.y;
+          v[4 * g + 2] = __uint_as_float(u[4 * g + 2]) + b4.z;
+          v[4 * g + 3] = __uint_as_float(u[4 * g + 3]) + b4.w;
+        }
+        if (p.rowadd) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            v[4 * g + 0] += ra[g].x; v[4 * g + 1] += ra[g].y; v[4 * g + 2] += ra[g].z; v[4 * g + 3] += ra[g].w;
+          }
+        }
+        const uint32_t st16 = st16_base + (chunk_ctr & 1) * kStage16Bytes;
+        if (geglu) {
+          // 32 accumulator columns = 16 (value, gate) pairs -> 16 outputs = 32 bytes per row (unswizzled staging)
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float o0 = v[4 * i + 0] * gelu_erf(v[4 * i + 1]) * p.out_scale;
+            const float o1 = v[4 * i + 2] * gelu_erf(v[4 * i + 3]) * p.out_scale;
+            w[i] = pack16(o0, o1, p.out_dtype == CTTA_BF16);
+          }
+          const uint32_t dst = st16 + lane * 32;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_out, st16, col >> 1, st_row, st_img);
+            tma_store_commit();
+            tma_store_wait_read<1>();
+          }
+          __syncwarp();
+          continue;
+        }
+        if (p.act != CTTA_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], p.act, p.act_slope);
+        }
+        // ---- fp32 inputs from the ring (residual, previous out)
+        uint32_t slot_addr = 0;
+        int first_slot = -1;
+        if (p.ring_slots > 0) {
+          for (int k = 0; k < p.ring_per_chunk; ++k) {
+            mbar_wait(smem_u32(&bar_ring_full[slot]), ring_phase);
+            const uint32_t sa = ring_base + slot * kRingSlotBytes + lr * 128;
+            if (k == 0) {
+              slot_addr = sa;
+              first_slot = slot;
+            }
+            if (k < p.ring_in) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                float4 r4;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(r4.x), "=f"(r4.y), "=f"(r4.z), "=f"(r4.w)
+                             : "r"(sa + ((g ^ sw7) << 4)));
+                v[4 * g + 0] += r4.x; v[4 * g + 1] += r4.y; v[4 * g + 2] += r4.z; v[4 * g + 3] += r4.w;
+              }
+            }
+            if (k > 0 || !out_f32) {
+              // slot only read: release it right away
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(&bar_ring_empty[slot]));
+            }
+            if (++slot == p.ring_slots) {
+              slot = 0;
+              ring_phase ^= 1u;
+            }
+          }
+        }
+        if (p.out_scale != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= p.out_scale;
+        }
+        if (out_f32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot_addr + ((g ^ sw7) << 4)),
+                         "f"(v[4 * g + 0]), "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3])
+                         : "memory");
+          }
+        }
+        if (out_16 || p.out2) {
+          const int bf = out_16 ? (p.out_dtype == CTTA_BF16) : p.is_bf16;
+          const uint32_t dst = st16 + lane * 64;
+          const int sw3 = (lane >> 1) & 3;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float w8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w8[i] = out_16 ? v[8 * g + i] : act_apply(v[8 * g + i], p.act2, p.act2_slope);
+            const uint32_t w0 = pack16(w8[0], w8[1], bf), w1 = pack16(w8[2], w8[3], bf);
+            const uint32_t w2 = pack16(w8[4], w8[5], bf), w3 = pack16(w8[6], w8[7], bf);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((g ^ sw3) << 4)), "r"(w0), "r"(w1),
+                         "r"(w2), "r"(w3)
+                         : "memory");
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (out_f32) tma_store_3d(&tmap_out, ring_base + first_slot * kRingSlotBytes + wrow * 128, col, st_row, st_img);
+          if (out_16) tma_store_3d(&tmap_out, st16, col, st_row, st_img);
+          if (p.out2) tma_store_3d(&tmap_out2, st16, col, st_row, st_img);
+          tma_store_commit();
+          tma_store_wait_read<1>();  // everything but the group just committed has finished reading smem
+          if (pending_slot >= 0) mbar_arrive(smem_u32(&bar_ring_empty[pending_slot]));
+        }
+        pending_slot = out_f32 ? first_slot : -1;
+        __syncwarp();
+      }
+    }
+    if (lane == 0) tma_store_wait_all();  // global writes complete before the CTA exits
   }
 
   tc_fence_before();
@@ -461,14 +735,16 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_tmap(CUtensorMap* m, int is_bf16, const void* base, int rank, const cuuint64_t* dims,
-                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+static int make_tmap_ex(CUtensorMap* m, int dtype, CUtensorMapSwizzle swz, const void* base, int rank,
+                        const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(CTTA_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
-                  const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = dtype == CTTA_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == CTTA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                      : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(m, dt, rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return set_error(CTTA_ERR_CUDA,
                      "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]",
@@ -479,7 +755,26 @@ static int make_tmap(CUtensorMap* m, int is_bf16, const void* base, int rank, co
   return 0;
 }
 
+static int make_tmap(CUtensorMap* m, int is_bf16, const void* base, int rank, const cuuint64_t* dims,
+                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  return make_tmap_ex(m, is_bf16 ? CTTA_BF16 : CTTA_F16, CU_TENSOR_MAP_SWIZZLE_128B, base, rank, dims, strides_bytes,
+                      box);
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Row-addressed epilogue tensor (out / out2 / residual) as a 3-D map {columns, rows of one image, images} with a
+// {box_cols x 32 rows x 1} box.  Transposed-conv phases write every out_stride-th row starting at first_row.
+static int make_row_tmap(CUtensorMap* m, int dtype, const void* base, long long ld, int ncols, long long first_row,
+                         long long row_step, long long n_rows, long long img_rows, int n_img, int box_cols,
+                         CUtensorMapSwizzle swz) {
+  const int esz = dtype == CTTA_F32 ? 4 : 2;
+  const char* b = reinterpret_cast<const char*>(base) + first_row * ld * esz;
+  cuuint64_t dims[3] = {(cuuint64_t)ncols, (cuuint64_t)(n_rows > 0 ? n_rows : 1), (cuuint64_t)n_img};
+  cuuint64_t strides[2] = {(cuuint64_t)(row_step * ld * esz), (cuuint64_t)(img_rows * ld * esz)};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, 1};
+  return make_tmap_ex(m, dtype, swz, b, 3, dims, strides, box);
+}
 
 }  // namespace ctta
 
@@ -508,9 +803,21 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   p.a_mode = d->a_mode;
   p.is_bf16 = d->ab_dtype == CTTA_BF16;
   p.N = d->n;
-  const int n_tiles_n = (d->n + 255) / 256;
-  int block_n = ((d->n + n_tiles_n - 1) / n_tiles_n + 15) / 16 * 16;
-  if (block_n < 16) block_n = 16;
+  int block_n;
+  if (d->n <= 16) {
+    block_n = 16;
+  } else {
+    // multiple of 32 (epilogue chunk) minimising the padded width; ties -> the wider tile
+    long long best = -1;
+    block_n = 32;
+    for (int bn = 256; bn >= 32; bn -= 32) {
+      const long long padded = static_cast<long long>((d->n + bn - 1) / bn) * bn;
+      if (best < 0 || padded < best) {
+        best = padded;
+        block_n = bn;
+      }
+    }
+  }
   p.block_n = block_n;
   p.n_tiles_n = (d->n + block_n - 1) / block_n;
   int acc_stride = 32;
@@ -520,15 +827,30 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   p.k_chunks = (d->c + kBlockK - 1) / kBlockK;
   p.ntaps = d->ntaps;
   p.stage_bytes = kATileBytes + block_n * kBlockK * 2;
-  int n_stages = kSmemBudget / p.stage_bytes;
-  if (n_stages > kMaxStages) n_stages = kMaxStages;
-  p.n_stages = n_stages;
   p.H = d->h;
   p.W = d->w;
   p.n_img = d->n_img;
-  p.rows_per_img = d->rows_per_img;
+  // Output rows r * out_stride + out_off < 0 are dropped by definition: skip them up front by starting the logical
+  // rows at q_start (the A taps shift by the same amount), so no tile ever maps to a negative output row.
+  int q_start = 0;
+  if (d->out_off < 0) {
+    CTTA_REQUIRE(d->out_stride >= 1 && d->a_mode == CTTA_A_CONV1D, "ctta_gemm: negative out_off needs CONV1D mode");
+    q_start = (-d->out_off + d->out_stride - 1) / d->out_stride;
+  }
+  CTTA_REQUIRE(d->out_stride >= 1, "ctta_gemm: out_stride must be >= 1");
+  const int eff_out_off = q_start * d->out_stride + d->out_off;
+  int eff_rows = d->rows_per_img - q_start;
+  {
+    // never compute rows whose output row lies past the end of the image
+    const long long max_rows = eff_out_off < d->out_rows_per_img
+                                   ? (static_cast<long long>(d->out_rows_per_img) - 1 - eff_out_off) / d->out_stride + 1
+                                   : 0;
+    if (eff_rows > max_rows) eff_rows = static_cast<int>(max_rows);
+  }
+  if (eff_rows <= 0) return 0;  // nothing to write
+  p.rows_per_img = eff_rows;
   for (int j = 0; j < d->ntaps; ++j) {
-    p.tap_d0[j] = d->tap_d0[j];
+    p.tap_d0[j] = static_cast<short>(d->tap_d0[j] + q_start);
     p.tap_d1[j] = d->tap_d1[j];
   }
 
@@ -536,14 +858,14 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   CUtensorMap tmap_a, tmap_b;
   const int esz = 2;
   if (d->a_mode == CTTA_A_ROWS) {
-    p.n_tiles_m = (d->rows_per_img + kBlockM - 1) / kBlockM;
+    p.n_tiles_m = (p.rows_per_img + kBlockM - 1) / kBlockM;
     cuuint64_t dims[2] = {(cuuint64_t)d->c, (cuuint64_t)d->rows_per_img};
     cuuint64_t strides[1] = {(cuuint64_t)d->a_ld * esz};
     cuuint32_t box[2] = {kBlockK, kBlockM};
     int rc = make_tmap(&tmap_a, p.is_bf16, d->a, 2, dims, strides, box);
     if (rc) return rc;
   } else if (d->a_mode == CTTA_A_CONV1D) {
-    p.tiles_per_img = (d->rows_per_img + kBlockM - 1) / kBlockM;
+    p.tiles_per_img = (p.rows_per_img + kBlockM - 1) / kBlockM;
     p.n_tiles_m = p.tiles_per_img * d->n_img;
     cuuint64_t dims[3] = {(cuuint64_t)d->c, (cuuint64_t)d->w, (cuuint64_t)d->n_img};
     cuuint64_t strides[2] = {(cuuint64_t)d->a_ld * esz, (cuuint64_t)d->a_ld * esz * (cuuint64_t)d->w};
@@ -599,7 +921,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   p.act2_slope = d->act2_slope;
   p.out_rows_per_img = d->out_rows_per_img;
   p.out_stride = d->out_stride;
-  p.out_off = d->out_off;
+  p.out_off = eff_out_off;
 
   bool vec = true;
   if (d->bias && !aligned16(d->bias)) vec = false;
@@ -612,7 +934,89 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     CTTA_REQUIRE(aligned16(d->out) && d->out_ld % 4 == 0 && (!d->bias || aligned16(d->bias)),
                  "ctta_gemm: GEGLU output must be 16-byte aligned with out_ld %% 4 == 0");
 
-  const int smem_bytes = p.n_stages * p.stage_bytes + 1024;
+  // ---- epilogue plan: TMA-staged whenever every row pitch is a multiple of 16 bytes
+  const int out_esz = d->out ? (d->out_dtype == CTTA_F32 ? 4 : 2) : 0;
+  bool tma_ok = d->n >= 32 && block_n % kChunkCols == 0;
+  if (d->out && ((static_cast<long long>(d->out_ld) * out_esz) % 16 || !aligned16(d->out))) tma_ok = false;
+  if (d->out2 && ((static_cast<long long>(d->out2_ld) * 2) % 16 || !aligned16(d->out2))) tma_ok = false;
+  if (d->residual && (d->res_dtype != CTTA_F32 || (static_cast<long long>(d->res_ld) * 4) % 16 || !aligned16(d->residual)))
+    tma_ok = false;
+  if (d->out && d->out_dtype != CTTA_F32 && d->out2) tma_ok = false;
+  if (d->accumulate && d->out_dtype != CTTA_F32) tma_ok = false;
+  if (d->act == CTTA_ACT_GEGLU && d->out_dtype == CTTA_F32) tma_ok = false;
+  if (d->bias && !((reinterpret_cast<uintptr_t>(d->bias) & 3) == 0)) tma_ok = false;
+  if (d->rowadd && (!aligned16(d->rowadd) || d->rowadd_ld % 4)) tma_ok = false;
+  int rows_tile_img = kBlockM;
+  if (d->a_mode == CTTA_A_CONV2D) {
+    rows_tile_img = kBlockM / p.box_n;
+    if (p.tiles_w != 1 || rows_tile_img % 32 != 0) tma_ok = false;
+  }
+  p.out_rows_tile_img = rows_tile_img;
+  p.epi_tma = tma_ok ? 1 : 0;
+  CUtensorMap tmap_out, tmap_out2, tmap_res;
+  memset(&tmap_out, 0, sizeof(tmap_out));
+  memset(&tmap_out2, 0, sizeof(tmap_out2));
+  memset(&tmap_res, 0, sizeof(tmap_res));
+  int ring_bytes = 0, st16_bytes = 0, bias_bytes = 0;
+  if (tma_ok) {
+    // geometry of the row maps (see ctta_gemm_desc: out row = r * out_stride + out_off, dropped outside the image)
+    const long long first_row = eff_out_off;
+    const long long n_rows = p.rows_per_img;
+    p.row_coord_shift = 0;
+    const bool geglu = d->act == CTTA_ACT_GEGLU;
+    if (d->out) {
+      const bool f32 = d->out_dtype == CTTA_F32;
+      int rc = make_row_tmap(&tmap_out, d->out_dtype, d->out, d->out_ld, geglu ? d->n / 2 : d->n, first_row,
+                             d->out_stride, n_rows, d->out_rows_per_img, d->n_img, geglu ? 16 : kChunkCols,
+                             f32 ? CU_TENSOR_MAP_SWIZZLE_128B : (geglu ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B));
+      if (rc) return rc;
+    }
+    if (d->out2) {
+      int rc = make_row_tmap(&tmap_out2, d->ab_dtype, d->out2, d->out2_ld, d->n, first_row, d->out_stride, n_rows,
+                             d->out_rows_per_img, d->n_img, kChunkCols, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+    if (d->residual) {
+      int rc = make_row_tmap(&tmap_res, CTTA_F32, d->residual, d->res_ld, d->n, first_row, d->out_stride, n_rows,
+                             d->out_rows_per_img, d->n_img, kChunkCols, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    p.ring_in = (d->residual ? 1 : 0) + (d->accumulate ? 1 : 0);
+    const bool out_f32 = d->out && d->out_dtype == CTTA_F32;
+    const bool use_ring = out_f32 || p.ring_in > 0;
+    p.ring_per_chunk = use_ring ? (p.ring_in > 1 ? p.ring_in : 1) : 0;
+    st16_bytes = ((d->out && !out_f32) || d->out2) ? 4 * 2 * kStage16Bytes : 0;
+    bias_bytes = kBiasBytes;
+    int stages = 0, ring = 0;
+    if (!use_ring) {
+      stages = (kSmemBudget - st16_bytes - bias_bytes) / p.stage_bytes;
+    } else {
+      const int need = 2 * p.ring_per_chunk;
+      for (int st = 4; st >= 2 && stages == 0; --st) {
+        int r = (kSmemBudget - st * p.stage_bytes - st16_bytes - bias_bytes) / kRingSlotBytes;
+        if (r > kMaxRing) r = kMaxRing;
+        const int want = st > 2 ? (need > 3 ? need : 3) : need;
+        if (r >= want) {
+          stages = st;
+          ring = r;
+        }
+      }
+      CTTA_REQUIRE(stages > 0, "ctta_gemm: shared-memory plan failed (block_n=%d)", block_n);
+      // spare room goes to mainloop stages first (up to 4), the rest to the ring
+    }
+    if (stages > kMaxStages) stages = kMaxStages;
+    p.n_stages = stages;
+    p.ring_slots = ring;
+    ring_bytes = ring * kRingSlotBytes;
+    p.ring_off = stages * p.stage_bytes;
+    p.stage16_off = p.ring_off + ring_bytes;
+    p.bias_off = p.stage16_off + st16_bytes;
+  } else {
+    int n_stages = kSmemBudget / p.stage_bytes;
+    if (n_stages > kMaxStages) n_stages = kMaxStages;
+    p.n_stages = n_stages;
+  }
+  const int smem_bytes = p.n_stages * p.stage_bytes + ring_bytes + st16_bytes + bias_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     CTTA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic));
@@ -621,7 +1025,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   int grid = sm_count();
   if (grid > total_tiles) grid = total_tiles;
-  gemm_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, p);
+  gemm_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, tmap_out, tmap_out2, tmap_res, p);
   CTTA_LAUNCH_CHECK();
   return 0;
 }
