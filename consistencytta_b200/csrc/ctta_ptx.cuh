@@ -154,6 +154,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same, for an operand whose first row is NOT on a 1024-byte boundary (a row-shifted view of a resident tile):
+// bits [49,52) "matrix base offset" = (start address >> 7) & 7, the row phase inside the 8-row swizzle pattern.
+__device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t smem_addr) {
+  return umma_desc_sw128(smem_addr) | (static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49);
+}
 // Instruction descriptor for kind::f16: fp32 accumulate, A/B both K-major, dense.
 //   [4,6) c_format (1 = f32)  [7,10) a_format  [10,13) b_format (0 = f16, 1 = bf16)
 //   [15] a_major [16] b_major (0 = K)  [17,23) N >> 3  [24,29) M >> 4

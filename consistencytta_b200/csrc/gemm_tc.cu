@@ -16,7 +16,10 @@
 //
 // Reference call sites replaced: see ctta_gemm in include/ctta.h.
 #include <cuda.h>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
 #include "ctta_internal.h"
 #include "ctta_ptx.cuh"
 
@@ -26,7 +29,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                         // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 224;
+constexpr int kThreads = 352;                        // 3 control warps + 8 epilogue warps
 constexpr int kSmemMaxDynamic = 232448 - 1024;     // 227 KiB minus the static barriers
 constexpr int kSmemBudget = kSmemMaxDynamic - 1024;  // minus alignment slack
 constexpr int kEpiWarp0 = 3;                         // first of the 4 epilogue math warps
@@ -34,6 +37,7 @@ constexpr int kChunkCols = 32;                       // accumulator columns per 
 constexpr int kRingSlotBytes = kBlockM * kChunkCols * 4;  // 16 KiB: 128 rows x 32 fp32 columns (128-B swizzle)
 constexpr int kMaxRing = 6;
 constexpr int kStage16Bytes = 32 * kChunkCols * 2;   // 2 KiB: 32 rows x 32 16-bit columns per warp per buffer
+constexpr int kEpiWarps = 8;                         // two warps per TMEM lane quarter, alternating chunks
 constexpr int kBiasBytes = 2 * 256 * 4;
 
 struct GemmKParams {
@@ -73,6 +77,13 @@ struct GemmKParams {
   int out_rows_tile_img;   // rows of one image inside a 128-row tile (128 / box_n)
   int row_coord_shift;     // logical row -> TMA row coordinate (transposed-conv phases start at q_start)
   int ring_off, stage16_off, bias_off;  // byte offsets from the 1024-aligned dynamic smem base
+  int kk_last;             // 16-wide K slices actually needed in the last channel chunk of a tap (1..4)
+  // halo mode (CONV1D, c <= 64, single N tile): all taps' weights stay resident in shared memory and every tile
+  // loads ONE halo'd activation box; tap j is a row-shifted UMMA view of it (no per-tap re-load from L2)
+  int halo, halo_rows, halo_min_shift, w_bytes, tiles_off;
+  // M super-tiles (ROWS / CONV1D with narrow N): one tile = sub_tiles x 128 rows sharing one accumulator stage,
+  // which amortises the per-tile hand-offs when a 128 x N tile is only a few hundred cycles of work
+  int sub_tiles;
 };
 
 struct TileCoord {
@@ -85,12 +96,12 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile)
   const int m_tile = tile / p.n_tiles_n;
   tc.n0 = (tile - m_tile * p.n_tiles_n) * p.block_n;
   if (p.a_mode == CTTA_A_ROWS) {
-    tc.c1 = m_tile * kBlockM;
+    tc.c1 = m_tile * kBlockM * p.sub_tiles;
     tc.c2 = 0;
     tc.c3 = 0;
   } else if (p.a_mode == CTTA_A_CONV1D) {
     const int b = m_tile / p.tiles_per_img;
-    tc.c1 = (m_tile - b * p.tiles_per_img) * kBlockM;
+    tc.c1 = (m_tile - b * p.tiles_per_img) * kBlockM * p.sub_tiles;
     tc.c2 = b;
     tc.c3 = 0;
   } else {
@@ -280,6 +291,24 @@ __device__ __forceinline__ void epilogue8(const GemmKParams& p, float* v, int co
   }
 }
 
+
+// Compile-time specialisation of the TMA-staged epilogue.  -1 = decided at run time (generic instance).
+template <int ACT, int ROWADD, int RING_IN, int OUT_F32, int OUT_16, int OUT2, int ACT2>
+struct EpiCfg {
+  static constexpr int kAct = ACT, kRowadd = ROWADD, kRingIn = RING_IN, kOutF32 = OUT_F32, kOut16 = OUT_16,
+                       kOut2 = OUT2, kAct2 = ACT2;
+};
+using EpiGeneric = EpiCfg<-1, -1, -1, -1, -1, -1, -1>;
+#define CTTA_CFG(field, runtime) (Cfg::field >= 0 ? Cfg::field : (runtime))
+
+// two fp32 -> packed f16x2 with saturation to the finite range, one instruction
+__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+template <class Cfg>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
@@ -291,6 +320,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __shared__ __align__(8) uint64_t bar_tmem_empty[2];
   __shared__ __align__(8) uint64_t bar_ring_full[kMaxRing];
   __shared__ __align__(8) uint64_t bar_ring_empty[kMaxRing];
+  __shared__ __align__(8) uint64_t bar_weights;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -304,12 +334,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tmem_full[s]), 1);
-      mbar_init(smem_u32(&bar_tmem_empty[s]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&bar_tmem_empty[s]), p.epi_tma ? kEpiWarps : 4);  // one arrive per epilogue warp
     }
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(smem_u32(&bar_ring_full[s]), 1);
       mbar_init(smem_u32(&bar_ring_empty[s]), 4);
     }
+    mbar_init(smem_u32(&bar_weights), 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -331,34 +362,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   const int k_iters = p.ntaps * p.k_chunks;
 
+  const uint32_t stages_base = tiles_base + static_cast<uint32_t>(p.tiles_off);
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane)
-    if (lane == 0) {
+    if (lane == 0 && p.halo) {
+      // resident weights: one {64 x block_n} box per tap, loaded once per CTA
+      const uint32_t wbar = smem_u32(&bar_weights);
+      mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(p.w_bytes));
+      for (int j = 0; j < p.ntaps; ++j)
+        tma_load_2d(tiles_base + static_cast<uint32_t>(j * p.block_n * 128), &tmap_b, wbar, j * kBlockK, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.halo_rows * 128);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        for (int sub = 0; sub < p.sub_tiles; ++sub) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          mbar_arrive_expect_tx(full, tx_bytes);
+          tma_load_3d(stages_base + static_cast<uint32_t>(stage * p.stage_bytes), &tmap_a, full, 0,
+                      tc.c1 + sub * kBlockM + p.halo_min_shift, tc.c2);
+          if (++stage == p.n_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = static_cast<uint32_t>(p.stage_bytes);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
-        int kb = 0;
-        for (int j = 0; j < p.ntaps; ++j) {
-          const int d0 = p.tap_d0[j], d1 = p.tap_d1[j];
-          for (int kc = 0; kc < p.k_chunks; ++kc, ++kb) {
-            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-            const uint32_t full = smem_u32(&bar_full[stage]);
-            mbar_arrive_expect_tx(full, tx_bytes);
-            const uint32_t a_dst = tiles_base + static_cast<uint32_t>(stage * p.stage_bytes);
-            const uint32_t b_dst = a_dst + kATileBytes;
-            if (p.a_mode == CTTA_A_ROWS) {
-              tma_load_2d(a_dst, &tmap_a, full, kc * kBlockK, tc.c1);
-            } else if (p.a_mode == CTTA_A_CONV1D) {
-              tma_load_3d(a_dst, &tmap_a, full, kc * kBlockK, tc.c1 + d0, tc.c2);
-            } else {
-              tma_load_4d(a_dst, &tmap_a, full, kc * kBlockK, tc.c1 + d0, tc.c2 + d1, tc.c3);
-            }
-            tma_load_2d(b_dst, &tmap_b, full, kb * kBlockK, tc.n0);
-            if (++stage == p.n_stages) {
-              stage = 0;
-              phase ^= 1u;
+        for (int sub = 0; sub < p.sub_tiles; ++sub) {
+          const int r0 = tc.c1 + sub * kBlockM;  // sub_tiles > 1 only in ROWS / CONV1D mode
+          int kb = 0;
+          for (int j = 0; j < p.ntaps; ++j) {
+            const int d0 = p.tap_d0[j], d1 = p.tap_d1[j];
+            for (int kc = 0; kc < p.k_chunks; ++kc, ++kb) {
+              mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+              const uint32_t full = smem_u32(&bar_full[stage]);
+              mbar_arrive_expect_tx(full, tx_bytes);
+              const uint32_t a_dst = stages_base + static_cast<uint32_t>(stage * p.stage_bytes);
+              const uint32_t b_dst = a_dst + kATileBytes;
+              if (p.a_mode == CTTA_A_ROWS) {
+                tma_load_2d(a_dst, &tmap_a, full, kc * kBlockK, r0);
+              } else if (p.a_mode == CTTA_A_CONV1D) {
+                tma_load_3d(a_dst, &tmap_a, full, kc * kBlockK, r0 + d0, tc.c2);
+              } else {
+                tma_load_4d(a_dst, &tmap_a, full, kc * kBlockK, tc.c1 + d0, tc.c2 + d1, tc.c3);
+              }
+              tma_load_2d(b_dst, &tmap_b, full, kb * kBlockK, tc.n0);
+              if (++stage == p.n_stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
             }
           }
         }
@@ -366,7 +424,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0) {
+    if (lane == 0 && p.halo) {
+      const uint32_t idesc = umma_idesc(kBlockM, p.block_n, p.is_bf16);
+      mbar_wait(smem_u32(&bar_weights), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
+        for (int sub = 0; sub < p.sub_tiles; ++sub) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride + sub * p.block_n);
+          const uint32_t a_base = stages_base + static_cast<uint32_t>(stage * p.stage_bytes);
+          for (int j = 0; j < p.ntaps; ++j) {
+            // tap j = the resident box shifted by (d_j - min_shift) rows of 128 bytes.  The swizzle phase is taken
+            // from the shared-memory address bits, so a row-shifted start needs no descriptor base offset.
+            const uint32_t a_addr = a_base + static_cast<uint32_t>((p.tap_d0[j] - p.halo_min_shift) * 128);
+            const uint32_t b_addr = tiles_base + static_cast<uint32_t>(j * p.block_n * 128);
+            for (int kk = 0; kk < p.kk_last; ++kk) {
+              umma_f16(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), idesc,
+                       (j | kk) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(&bar_empty[stage]));
+          if (++stage == p.n_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(smem_u32(&bar_tmem_full[acc]));
+      }
+    } else if (lane == 0) {
       const uint32_t idesc = umma_idesc(kBlockM, p.block_n, p.is_bf16);
       int stage = 0;
       uint32_t phase = 0;
@@ -376,22 +467,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
+        for (int sub = 0; sub < p.sub_tiles; ++sub) {
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride + sub * p.block_n);
+        int kc = 0;
         for (int kb = 0; kb < k_iters; ++kb) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
           tc_fence_after();
-          const uint32_t a_addr = tiles_base + static_cast<uint32_t>(stage * p.stage_bytes);
+          const uint32_t a_addr = stages_base + static_cast<uint32_t>(stage * p.stage_bytes);
           const uint32_t b_addr = a_addr + kATileBytes;
+          const int nkk = (kc == p.k_chunks - 1) ? p.kk_last : kBlockK / 16;  // skip all-zero K slices
 #pragma unroll
           for (int kk = 0; kk < kBlockK / 16; ++kk) {
-            umma_f16(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), idesc,
-                     (kb | kk) != 0 ? 1u : 0u);
+            if (kk < nkk)
+              umma_f16(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), idesc,
+                       (kb | kk) != 0 ? 1u : 0u);
           }
           umma_commit(smem_u32(&bar_empty[stage]));  // frees the smem stage once these MMAs retire
+          if (++kc == p.k_chunks) kc = 0;
           if (++stage == p.n_stages) {
             stage = 0;
             phase ^= 1u;
           }
+        }
         }
         umma_commit(smem_u32(&bar_tmem_full[acc]));  // accumulator complete -> epilogue
       }
@@ -416,8 +513,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           row0 = tc.c2 * p.W + tc.c1; img0 = tc.c3;
         }
         row0 -= p.row_coord_shift;
-        for (int ch = 0; ch < n_chunks; ++ch) {
+        for (int cc = 0; cc < n_chunks * p.sub_tiles; ++cc) {
+          const int sub = cc / n_chunks;
+          const int ch = cc - sub * n_chunks;
           const int col = tc.n0 + ch * kChunkCols;
+          const int srow0 = row0 + sub * kBlockM;
           for (int k = 0; k < p.ring_per_chunk; ++k) {
             mbar_wait(smem_u32(&bar_ring_empty[slot]), phase ^ 1u);
             const uint32_t full = smem_u32(&bar_ring_full[slot]);
@@ -431,7 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int qq = 0; qq < 4; ++qq) {
                 const int wr = qq * 32;
                 tma_load_3d(ring_base + slot * kRingSlotBytes + wr * 128, map, full, col,
-                            row0 + (wr % p.out_rows_tile_img), img0 + wr / p.out_rows_tile_img);
+                            srow0 + (wr % p.out_rows_tile_img), img0 + wr / p.out_rows_tile_img);
               }
             } else {
               mbar_arrive(full);
@@ -445,6 +545,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (!p.epi_tma) {
+   if (warp < kEpiWarp0 + 4) {
     // ------------------------------------------------------------------ epilogue warps, direct global access
     // (tiny / unaligned outputs: N <= 16 or row pitch not a multiple of 16 bytes)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -511,27 +612,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
+   }
   } else {
     // ------------------------------------------------------------------ epilogue warps, TMA-staged
-    // thread = accumulator row.  Per 32-column chunk: TMEM -> registers, + bias (smem broadcast) + rowadd, act,
-    // + residual / previous out (ring slot, prefetched by warp 2), scale; fp32 result written back in place into
-    // the ring slot, 16-bit results into the per-warp staging buffer; one lane issues the TMA stores.
+    // thread = accumulator row.  Two warps per TMEM lane quarter (group 0 / 1) take alternate 32-column chunks.
+    // Per chunk: TMEM -> registers, + bias (smem broadcast) + rowadd, act, + residual / previous out (ring slot,
+    // prefetched by warp 2), scale; the fp32 result is written back in place into the ring slot, 16-bit results
+    // into the per-warp staging buffer; one lane issues the TMA stores.
+    const int has_rowadd = CTTA_CFG(kRowadd, p.rowadd != nullptr ? 1 : 0);
+    const int ring_in = CTTA_CFG(kRingIn, p.ring_in);
+    const int out_f32 = CTTA_CFG(kOutF32, (p.out != nullptr && p.out_dtype == CTTA_F32) ? 1 : 0);
+    const int out_16 = CTTA_CFG(kOut16, (p.out != nullptr && p.out_dtype != CTTA_F32) ? 1 : 0);
+    const int has_out2 = CTTA_CFG(kOut2, p.out2 != nullptr ? 1 : 0);
+    const int act = CTTA_CFG(kAct, p.act);
+    const int act2 = CTTA_CFG(kAct2, p.act2);
+    const bool generic = Cfg::kAct < 0;       // only the generic instance supports bf16 outputs
+    const int ring_per_chunk = (out_f32 || ring_in > 0) ? (ring_in > 1 ? ring_in : 1) : 0;
+
     const int q = warp & 3;
-    const int ew = warp - kEpiWarp0;          // 0..3, owner of staging buffers
+    const int ew = warp - kEpiWarp0;          // 0..7, owner of staging buffers
+    const int grp = ew >> 2;                  // chunk parity handled by this warp
     const int lr = q * 32 + lane;             // row inside the tile
     const int n_chunks = p.block_n / kChunkCols;
+    const int tot_chunks = n_chunks * p.sub_tiles;
     const uint32_t ring_base = tiles_base + static_cast<uint32_t>(p.ring_off);
     const uint32_t st16_base = tiles_base + static_cast<uint32_t>(p.stage16_off) + ew * 2 * kStage16Bytes;
     float* bias_s = reinterpret_cast<float*>(smem_raw + (tiles_base - smem_u32(smem_raw)) + p.bias_off);
-    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
-    const bool out_f32 = p.out != nullptr && p.out_dtype == CTTA_F32;
-    const bool out_16 = p.out != nullptr && p.out_dtype != CTTA_F32;
-    const bool geglu = p.act == CTTA_ACT_GEGLU;
+    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..255
     const int sw7 = lane & 7;
-    int slot = 0;
-    uint32_t ring_phase = 0;
+    const int wrow = q * 32;
+    const int wrow_in_img = wrow % p.out_rows_tile_img;
+    const int wimg = wrow / p.out_rows_tile_img;
     int pending_slot = -1;  // ring slot whose TMA store may still be reading shared memory
-    uint32_t chunk_ctr = 0;
+    uint32_t my_ctr = 0;    // chunks processed by this warp (staging buffer parity)
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -545,12 +658,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       } else {
         row0 = tc.c2 * p.W + tc.c1; img0 = tc.c3;
       }
-      // this warp's 32 rows: coordinates of the store box
-      const int wrow = q * 32;
-      const int st_row = row0 + (wrow % p.out_rows_tile_img) - p.row_coord_shift;
-      const int st_img = img0 + wrow / p.out_rows_tile_img;
+      // this warp's 32 rows: coordinates of the store box (of sub-tile 0)
+      const int st_row0 = row0 + wrow_in_img - p.row_coord_shift;
+      const int st_img = img0 + wimg;
       long long ra_row = 0;
-      if (p.rowadd) {
+      if (has_rowadd) {  // (host guarantees sub_tiles == 1 with rowadd)
         const int r_in_img = (p.a_mode == CTTA_A_CONV2D) ? (row0 + (lr % p.out_rows_tile_img)) : (row0 + lr);
         const int img = (p.a_mode == CTTA_A_CONV2D) ? (img0 + lr / p.out_rows_tile_img) : img0;
         long long gr = static_cast<long long>(img) * p.rows_per_img + r_in_img;
@@ -560,23 +672,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       // bias of this tile -> shared memory (double buffered by tile parity)
       float* bs = bias_s + (it & 1) * 256;
-      for (int i = et; i < p.block_n; i += 128) {
+      for (int i = et; i < p.block_n; i += kEpiWarps * 32) {
         const int c = tc.n0 + i;
         bs[i] = (p.bias != nullptr && c < p.N) ? p.bias[c] : 0.f;
       }
-      named_barrier_sync(1, 128);
+      named_barrier_sync(1, kEpiWarps * 32);
 
       mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
-      for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
+      const long long chunk_base = static_cast<long long>(it) * tot_chunks;
+      const int last_cc = ((tot_chunks - 1 - grp) / 2) * 2 + grp;  // last chunk of this group (may be < 0 .. handled)
+      if (grp >= tot_chunks) {
+        // nothing to read from this accumulator stage
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+      }
+      int sub = 0, ch = grp;
+      while (ch >= n_chunks) { ch -= n_chunks; ++sub; }
+      for (int cc = grp; cc < tot_chunks; cc += 2, ++my_ctr) {
         const int c0 = ch * kChunkCols;
         const int col = tc.n0 + c0;
+        const int st_row = st_row0 + sub * kBlockM;
         uint32_t u[32];
-        tmem_ld_x32(t_addr + c0, u);
+        tmem_ld_x32(t_addr + sub * p.block_n + c0, u);
         // per-row additive term (time embedding): issue the loads before waiting on TMEM / the ring
         float4 ra[8];
-        if (p.rowadd) {
+        if (has_rowadd) {
           const float* rp = p.rowadd + ra_row * p.rowadd_ld + col;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -585,7 +707,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         tmem_ld_wait();
-        if (ch == n_chunks - 1) {
+        if (cc == last_cc) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
@@ -599,21 +721,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           v[4 * g + 2] = __uint_as_float(u[4 * g + 2]) + b4.z;
           v[4 * g + 3] = __uint_as_float(u[4 * g + 3]) + b4.w;
         }
-        if (p.rowadd) {
+        if (has_rowadd) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             v[4 * g + 0] += ra[g].x; v[4 * g + 1] += ra[g].y; v[4 * g + 2] += ra[g].z; v[4 * g + 3] += ra[g].w;
           }
         }
-        const uint32_t st16 = st16_base + (chunk_ctr & 1) * kStage16Bytes;
-        if (geglu) {
+        const uint32_t st16 = st16_base + (my_ctr & 1) * kStage16Bytes;
+        if (act == CTTA_ACT_GEGLU) {
           // 32 accumulator columns = 16 (value, gate) pairs -> 16 outputs = 32 bytes per row (unswizzled staging)
           uint32_t w[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float o0 = v[4 * i + 0] * gelu_erf(v[4 * i + 1]) * p.out_scale;
             const float o1 = v[4 * i + 2] * gelu_erf(v[4 * i + 3]) * p.out_scale;
-            w[i] = pack16(o0, o1, p.out_dtype == CTTA_BF16);
+            w[i] = (generic && p.out_dtype == CTTA_BF16) ? pack16(o0, o1, 1) : pack_f16_sat(o0, o1);
           }
           const uint32_t dst = st16 + lane * 32;
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
@@ -626,84 +748,101 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tma_store_wait_read<1>();
           }
           __syncwarp();
-          continue;
-        }
-        if (p.act != CTTA_ACT_NONE) {
+        } else {
+          if (act != CTTA_ACT_NONE) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], p.act, p.act_slope);
-        }
-        // ---- fp32 inputs from the ring (residual, previous out)
-        uint32_t slot_addr = 0;
-        int first_slot = -1;
-        if (p.ring_slots > 0) {
-          for (int k = 0; k < p.ring_per_chunk; ++k) {
-            mbar_wait(smem_u32(&bar_ring_full[slot]), ring_phase);
-            const uint32_t sa = ring_base + slot * kRingSlotBytes + lr * 128;
-            if (k == 0) {
-              slot_addr = sa;
-              first_slot = slot;
-            }
-            if (k < p.ring_in) {
+            for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], act, p.act_slope);
+          }
+          // ---- fp32 inputs from the ring (residual, previous out)
+          uint32_t slot_addr = 0;
+          int first_slot = -1;
+          if (ring_per_chunk > 0) {
+            const long long s0 = (chunk_base + cc) * ring_per_chunk;
+            for (int k = 0; k < ring_per_chunk; ++k) {
+              const long long sidx = s0 + k;
+              const int slot = static_cast<int>(sidx % p.ring_slots);
+              const uint32_t ring_phase = static_cast<uint32_t>((sidx / p.ring_slots) & 1);
+              mbar_wait(smem_u32(&bar_ring_full[slot]), ring_phase);
+              const uint32_t sa = ring_base + slot * kRingSlotBytes + lr * 128;
+              if (k == 0) {
+                slot_addr = sa;
+                first_slot = slot;
+              }
+              if (k < ring_in) {
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                float4 r4;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(r4.x), "=f"(r4.y), "=f"(r4.z), "=f"(r4.w)
-                             : "r"(sa + ((g ^ sw7) << 4)));
-                v[4 * g + 0] += r4.x; v[4 * g + 1] += r4.y; v[4 * g + 2] += r4.z; v[4 * g + 3] += r4.w;
+                for (int g = 0; g < 8; ++g) {
+                  float4 r4;
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                               : "=f"(r4.x), "=f"(r4.y), "=f"(r4.z), "=f"(r4.w)
+                               : "r"(sa + ((g ^ sw7) << 4)));
+                  v[4 * g + 0] += r4.x; v[4 * g + 1] += r4.y; v[4 * g + 2] += r4.z; v[4 * g + 3] += r4.w;
+                }
+              }
+              if (k > 0 || !out_f32) {
+                // slot only read: release it right away
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_ring_empty[slot]));
               }
             }
-            if (k > 0 || !out_f32) {
-              // slot only read: release it right away
-              __syncwarp();
-              if (lane == 0) mbar_arrive(smem_u32(&bar_ring_empty[slot]));
+          }
+          if (p.out_scale != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= p.out_scale;
+          }
+          if (out_f32) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot_addr + ((g ^ sw7) << 4)),
+                           "f"(v[4 * g + 0]), "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3])
+                           : "memory");
             }
-            if (++slot == p.ring_slots) {
-              slot = 0;
-              ring_phase ^= 1u;
+          }
+          if (out_16 || has_out2) {
+            const bool bf = generic && (out_16 ? (p.out_dtype == CTTA_BF16) : (p.is_bf16 != 0));
+            const uint32_t dst = st16 + lane * 64;
+            const int sw3 = (lane >> 1) & 3;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float w8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) w8[i] = out_16 ? v[8 * g + i] : act_apply(v[8 * g + i], act2, p.act2_slope);
+              uint32_t w0, w1, w2, w3;
+              if (bf) {
+                w0 = pack16(w8[0], w8[1], 1); w1 = pack16(w8[2], w8[3], 1);
+                w2 = pack16(w8[4], w8[5], 1); w3 = pack16(w8[6], w8[7], 1);
+              } else {
+                w0 = pack_f16_sat(w8[0], w8[1]); w1 = pack_f16_sat(w8[2], w8[3]);
+                w2 = pack_f16_sat(w8[4], w8[5]); w3 = pack_f16_sat(w8[6], w8[7]);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((g ^ sw3) << 4)), "r"(w0), "r"(w1),
+                           "r"(w2), "r"(w3)
+                           : "memory");
             }
           }
-        }
-        if (p.out_scale != 1.f) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= p.out_scale;
-        }
-        if (out_f32) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot_addr + ((g ^ sw7) << 4)),
-                         "f"(v[4 * g + 0]), "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3])
-                         : "memory");
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (out_f32) tma_store_3d(&tmap_out, ring_base + first_slot * kRingSlotBytes + wrow * 128, col, st_row, st_img);
+            if (out_16) tma_store_3d(&tmap_out, st16, col, st_row, st_img);
+            if (has_out2) tma_store_3d(&tmap_out2, st16, col, st_row, st_img);
+            tma_store_commit();
+            if (ring_in > 1) {
+              // two fp32 inputs per chunk (residual + accumulate): the ring is too shallow to keep a slot pending,
+              // so wait for this store's shared-memory reads and release the slot immediately
+              tma_store_wait_read<0>();
+              if (pending_slot >= 0) mbar_arrive(smem_u32(&bar_ring_empty[pending_slot]));
+              if (out_f32) mbar_arrive(smem_u32(&bar_ring_empty[first_slot]));
+            } else {
+              tma_store_wait_read<1>();  // everything but the group just committed has finished reading smem
+              if (pending_slot >= 0) mbar_arrive(smem_u32(&bar_ring_empty[pending_slot]));
+            }
           }
+          pending_slot = (out_f32 && ring_in <= 1) ? first_slot : -1;
+          __syncwarp();
         }
-        if (out_16 || p.out2) {
-          const int bf = out_16 ? (p.out_dtype == CTTA_BF16) : p.is_bf16;
-          const uint32_t dst = st16 + lane * 64;
-          const int sw3 = (lane >> 1) & 3;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float w8[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) w8[i] = out_16 ? v[8 * g + i] : act_apply(v[8 * g + i], p.act2, p.act2_slope);
-            const uint32_t w0 = pack16(w8[0], w8[1], bf), w1 = pack16(w8[2], w8[3], bf);
-            const uint32_t w2 = pack16(w8[4], w8[5], bf), w3 = pack16(w8[6], w8[7], bf);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((g ^ sw3) << 4)), "r"(w0), "r"(w1),
-                         "r"(w2), "r"(w3)
-                         : "memory");
-          }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          if (out_f32) tma_store_3d(&tmap_out, ring_base + first_slot * kRingSlotBytes + wrow * 128, col, st_row, st_img);
-          if (out_16) tma_store_3d(&tmap_out, st16, col, st_row, st_img);
-          if (p.out2) tma_store_3d(&tmap_out2, st16, col, st_row, st_img);
-          tma_store_commit();
-          tma_store_wait_read<1>();  // everything but the group just committed has finished reading smem
-          if (pending_slot >= 0) mbar_arrive(smem_u32(&bar_ring_empty[pending_slot]));
-        }
-        pending_slot = out_f32 ? first_slot : -1;
-        __syncwarp();
+        // advance (sub, ch) by two chunks
+        ch += 2;
+        while (ch >= n_chunks) { ch -= n_chunks; ++sub; }
       }
     }
     if (lane == 0) tma_store_wait_all();  // global writes complete before the CTA exits
@@ -826,6 +965,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   p.tmem_cols = 2 * acc_stride;
   p.k_chunks = (d->c + kBlockK - 1) / kBlockK;
   p.ntaps = d->ntaps;
+  p.kk_last = (d->c - (p.k_chunks - 1) * kBlockK + 15) / 16;
   p.stage_bytes = kATileBytes + block_n * kBlockK * 2;
   p.H = d->h;
   p.W = d->w;
@@ -867,9 +1007,26 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   } else if (d->a_mode == CTTA_A_CONV1D) {
     p.tiles_per_img = (p.rows_per_img + kBlockM - 1) / kBlockM;
     p.n_tiles_m = p.tiles_per_img * d->n_img;
+    // halo mode: one activation box with all the rows any tap needs, weights of all taps resident in smem
+    int min_shift = p.tap_d0[0], max_shift = p.tap_d0[0];
+    for (int j = 1; j < d->ntaps; ++j) {
+      if (p.tap_d0[j] < min_shift) min_shift = p.tap_d0[j];
+      if (p.tap_d0[j] > max_shift) max_shift = p.tap_d0[j];
+    }
+    const int halo_rows = (kBlockM + (max_shift - min_shift) + 7) / 8 * 8;
+    const int w_bytes = d->ntaps * block_n * 128;
+    const bool halo_env = getenv("CTTA_NO_HALO") == nullptr;
+    if (halo_env && p.k_chunks == 1 && p.n_tiles_n == 1 && halo_rows <= 256 && d->ntaps > 1 && w_bytes <= 96 * 1024) {
+      p.halo = 1;
+      p.halo_rows = halo_rows;
+      p.halo_min_shift = min_shift;
+      p.w_bytes = w_bytes;
+      p.tiles_off = (w_bytes + 1023) / 1024 * 1024;
+      p.stage_bytes = (halo_rows * 128 + 1023) / 1024 * 1024;
+    }
     cuuint64_t dims[3] = {(cuuint64_t)d->c, (cuuint64_t)d->w, (cuuint64_t)d->n_img};
     cuuint64_t strides[2] = {(cuuint64_t)d->a_ld * esz, (cuuint64_t)d->a_ld * esz * (cuuint64_t)d->w};
-    cuuint32_t box[3] = {kBlockK, kBlockM, 1};
+    cuuint32_t box[3] = {kBlockK, (cuuint32_t)(p.halo ? halo_rows : kBlockM), 1};
     int rc = make_tmap(&tmap_a, p.is_bf16, d->a, 3, dims, strides, box);
     if (rc) return rc;
   } else {
@@ -953,6 +1110,25 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   }
   p.out_rows_tile_img = rows_tile_img;
   p.epi_tma = tma_ok ? 1 : 0;
+  // M super-tiles for narrow N (see GemmKParams::sub_tiles)
+  p.sub_tiles = 1;
+  if (tma_ok && d->a_mode != CTTA_A_CONV2D && !d->rowadd && block_n <= 128 && getenv("CTTA_NO_SUPERTILE") == nullptr) {
+    int st = 256 / block_n;
+    if (st > 4) st = 4;
+    const long long row_tiles = (p.rows_per_img + kBlockM - 1) / kBlockM;
+    while (st > 1 && ((row_tiles + st - 1) / st) * d->n_img * p.n_tiles_n < 2LL * sm_count()) st /= 2;
+    p.sub_tiles = st;
+    if (d->a_mode == CTTA_A_ROWS) {
+      p.n_tiles_m = static_cast<int>((row_tiles + st - 1) / st);
+    } else {
+      p.tiles_per_img = static_cast<int>((row_tiles + st - 1) / st);
+      p.n_tiles_m = p.tiles_per_img * d->n_img;
+    }
+    int acc = 32;
+    while (acc < st * block_n) acc *= 2;
+    p.acc_stride = acc;
+    p.tmem_cols = 2 * acc;
+  }
   CUtensorMap tmap_out, tmap_out2, tmap_res;
   memset(&tmap_out, 0, sizeof(tmap_out));
   memset(&tmap_out2, 0, sizeof(tmap_out2));
@@ -985,47 +1161,96 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     const bool out_f32 = d->out && d->out_dtype == CTTA_F32;
     const bool use_ring = out_f32 || p.ring_in > 0;
     p.ring_per_chunk = use_ring ? (p.ring_in > 1 ? p.ring_in : 1) : 0;
-    st16_bytes = ((d->out && !out_f32) || d->out2) ? 4 * 2 * kStage16Bytes : 0;
+    st16_bytes = ((d->out && !out_f32) || d->out2) ? kEpiWarps * 2 * kStage16Bytes : 0;
     bias_bytes = kBiasBytes;
+    const int budget = kSmemBudget - p.tiles_off - st16_bytes - bias_bytes;
     int stages = 0, ring = 0;
     if (!use_ring) {
-      stages = (kSmemBudget - st16_bytes - bias_bytes) / p.stage_bytes;
+      stages = budget / p.stage_bytes;
     } else {
-      const int need = 2 * p.ring_per_chunk;
-      for (int st = 4; st >= 2 && stages == 0; --st) {
-        int r = (kSmemBudget - st * p.stage_bytes - st16_bytes - bias_bytes) / kRingSlotBytes;
-        if (r > kMaxRing) r = kMaxRing;
-        const int want = st > 2 ? (need > 3 ? need : 3) : need;
-        if (r >= want) {
+      // ring depth hides the residual-load latency, mainloop stages hide the operand-load latency: prefer a ring
+      // of 4 (>= 2 chunks in flight per input), then 3, then the minimum, as long as >= 3 mainloop stages remain
+      // a slot that is also the TMA-store source is released one chunk late by each of the two warp groups
+      const int need = ((out_f32 && p.ring_in < 2) ? 3 : 2) * p.ring_per_chunk;
+      const int prefs[3] = {need > 4 ? need : 4, need > 3 ? need : 3, need};
+      for (int i = 0; i < 3 && stages == 0; ++i) {
+        const int st = (budget - prefs[i] * kRingSlotBytes) / p.stage_bytes;
+        if (st >= 3 || (i == 2 && st >= 2)) {
           stages = st;
-          ring = r;
+          ring = prefs[i];
         }
       }
       CTTA_REQUIRE(stages > 0, "ctta_gemm: shared-memory plan failed (block_n=%d)", block_n);
-      // spare room goes to mainloop stages first (up to 4), the rest to the ring
     }
     if (stages > kMaxStages) stages = kMaxStages;
+    CTTA_REQUIRE(stages >= 2, "ctta_gemm: shared-memory plan failed (block_n=%d, stages=%d)", block_n, stages);
+    if (use_ring) {
+      // leftover room extends the ring
+      int extra = (budget - stages * p.stage_bytes - ring * kRingSlotBytes) / kRingSlotBytes;
+      ring += extra;
+      if (ring > kMaxRing) ring = kMaxRing;
+    }
     p.n_stages = stages;
     p.ring_slots = ring;
     ring_bytes = ring * kRingSlotBytes;
-    p.ring_off = stages * p.stage_bytes;
+    p.ring_off = p.tiles_off + stages * p.stage_bytes;
     p.stage16_off = p.ring_off + ring_bytes;
     p.bias_off = p.stage16_off + st16_bytes;
   } else {
-    int n_stages = kSmemBudget / p.stage_bytes;
+    int n_stages = (kSmemBudget - p.tiles_off) / p.stage_bytes;
     if (n_stages > kMaxStages) n_stages = kMaxStages;
     p.n_stages = n_stages;
   }
-  const int smem_bytes = p.n_stages * p.stage_bytes + ring_bytes + st16_bytes + bias_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CTTA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic));
-    attr_set = true;
-  }
+  const int smem_bytes = p.tiles_off + p.n_stages * p.stage_bytes + ring_bytes + st16_bytes + bias_bytes + 1024;
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   int grid = sm_count();
   if (grid > total_tiles) grid = total_tiles;
-  gemm_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, tmap_out, tmap_out2, tmap_res, p);
+
+  // ---- pick the compile-time specialised epilogue instance (fp16 operands / outputs only), else the generic one
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                           const CUtensorMap, const GemmKParams);
+  struct Variant {
+    int act, rowadd, ring_in, out_f32, out_16, out2, act2;
+    KernelFn fn;
+  };
+  constexpr int N_ = CTTA_ACT_NONE, L_ = CTTA_ACT_LRELU, G_ = CTTA_ACT_GEGLU;
+  static const Variant variants[] = {
+      {N_, 0, 0, 0, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 0, 0, 0, 1, L_>>},  // conv -> lrelu'ed 16-bit operand
+      {N_, 0, 1, 1, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 1, 1, 0, 1, L_>>},  // + residual, fp32 stream + operand
+      {N_, 0, 2, 1, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 2, 1, 0, 1, L_>>},  // + accumulate
+      {N_, 0, 2, 1, 0, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 2, 1, 0, 0, N_>>},
+      {N_, 0, 0, 1, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 0, 1, 0, 1, L_>>},  // transposed conv
+      {N_, 0, 1, 1, 0, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 1, 1, 0, 0, N_>>},  // fp32 out + residual
+      {N_, 1, 0, 1, 0, 0, N_, gemm_tc_kernel<EpiCfg<N_, 1, 0, 1, 0, 0, N_>>},  // fp32 out + time embedding
+      {N_, 0, 0, 1, 0, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 0, 1, 0, 0, N_>>},  // fp32 out
+      {N_, 0, 0, 0, 1, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 0, 0, 1, 0, N_>>},  // 16-bit out
+      {N_, 0, 1, 0, 1, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 1, 0, 1, 0, N_>>},  // 16-bit out + fp32 residual
+      {G_, 0, 0, 0, 1, 0, N_, gemm_tc_kernel<EpiCfg<G_, 0, 0, 0, 1, 0, N_>>},  // GEGLU
+  };
+  KernelFn fn = gemm_tc_kernel<EpiGeneric>;
+  if (p.epi_tma && !p.is_bf16 && d->out_dtype != CTTA_BF16 && getenv("CTTA_GENERIC_EPILOGUE") == nullptr) {
+    const int k_act = d->act, k_rowadd = d->rowadd ? 1 : 0, k_ring = p.ring_in;
+    const int k_f32 = (d->out && d->out_dtype == CTTA_F32) ? 1 : 0, k_16 = (d->out && d->out_dtype != CTTA_F32) ? 1 : 0;
+    const int k_out2 = d->out2 ? 1 : 0, k_act2 = d->out2 ? d->act2 : CTTA_ACT_NONE;
+    for (const Variant& v : variants) {
+      if (v.act == k_act && v.rowadd == k_rowadd && v.ring_in == k_ring && v.out_f32 == k_f32 && v.out_16 == k_16 &&
+          v.out2 == k_out2 && v.act2 == k_act2) {
+        fn = v.fn;
+        break;
+      }
+    }
+  }
+  {
+    static std::mutex mu;
+    static std::set<const void*> configured;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!configured.count(reinterpret_cast<const void*>(fn))) {
+      CTTA_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSmemMaxDynamic));
+      configured.insert(reinterpret_cast<const void*>(fn));
+    }
+  }
+  fn<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, tmap_out, tmap_out2, tmap_res, p);
   CTTA_LAUNCH_CHECK();
   return 0;
 }
