@@ -48,6 +48,7 @@ SIGNATURES = {
     "ctta_small_linear": (C.c_int, [_P, _I32, _I32, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "ctta_wave_minmax": (C.c_int, [_P, _I64, _P, _P]),
     "ctta_wave_to_int16": (C.c_int, [_P, _I64, _P, _P, _P]),
+    "ctta_lrelu_cast": (C.c_int, [_P, _I64, _F, _P, _I32, _P]),
     "ctta_cfg_mix": (C.c_int, [_P, _I64, _F, _P, _P]),
 }
 

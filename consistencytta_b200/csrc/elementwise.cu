@@ -194,6 +194,22 @@ __global__ void __launch_bounds__(256) cfg_mix_kernel(const float* __restrict__ 
   }
 }
 
+__global__ void __launch_bounds__(256) lrelu_cast_kernel(const float4* __restrict__ x, long long n4, float slope,
+                                                         uint2* __restrict__ y, int y_dtype) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 f = x[i];
+    f.x = f.x > 0.f ? f.x : f.x * slope;
+    f.y = f.y > 0.f ? f.y : f.y * slope;
+    f.z = f.z > 0.f ? f.z : f.z * slope;
+    f.w = f.w > 0.f ? f.w : f.w * slope;
+    uint2 u;
+    u.x = static_cast<uint32_t>(cvt16e(f.x, y_dtype)) | (static_cast<uint32_t>(cvt16e(f.y, y_dtype)) << 16);
+    u.y = static_cast<uint32_t>(cvt16e(f.z, y_dtype)) | (static_cast<uint32_t>(cvt16e(f.w, y_dtype)) << 16);
+    y[i] = u;
+  }
+}
+
 static int grid_for(long long total, int block) {
   long long b = (total + block - 1) / block;
   const long long cap = static_cast<long long>(sm_count()) * 16;
@@ -269,6 +285,18 @@ extern "C" int ctta_wave_to_int16(const float* wav, int64_t numel, const float* 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   CTTA_REQUIRE(wav && minmax && out && numel > 0, "wave_to_int16: bad arguments");
   to_int16_kernel<<<grid_for(numel, 256 * 4), 256, 0, stream>>>(wav, numel, minmax, out);
+  CTTA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ctta_lrelu_cast(const float* x, int64_t numel, float slope, void* y, int32_t y_dtype, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  CTTA_REQUIRE(x && y && numel > 0 && numel % 4 == 0, "lrelu_cast: numel must be a positive multiple of 4");
+  CTTA_REQUIRE(y_dtype == CTTA_F16 || y_dtype == CTTA_BF16, "lrelu_cast: 16-bit output only");
+  CTTA_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
+               "lrelu_cast: misaligned tensors");
+  lrelu_cast_kernel<<<grid_for(numel / 4, 256 * 4), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), numel / 4, slope,
+                                                                    reinterpret_cast<uint2*>(y), y_dtype);
   CTTA_LAUNCH_CHECK();
   return 0;
 }

@@ -84,6 +84,7 @@ struct GemmKParams {
   // M super-tiles (ROWS / CONV1D with narrow N): one tile = sub_tiles x 128 rows sharing one accumulator stage,
   // which amortises the per-tile hand-offs when a 128 x N tile is only a few hundred cycles of work
   int sub_tiles;
+  int epi_groups;          // 1 or 2 groups of 4 epilogue warps (2 = alternate chunks between the groups)
 };
 
 struct TileCoord {
@@ -217,6 +218,10 @@ __device__ __forceinline__ void epilogue8(const GemmKParams& p, float* v, int co
       }
     }
     const long long ooff = orow * p.out_ld + col;
+    if (p.out_scale != 1.f) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= p.out_scale;
+    }
     if (p.accumulate) {
       if (p.out_dtype == CTTA_F32) {
         const float* r = reinterpret_cast<const float*>(p.out) + ooff;
@@ -231,10 +236,6 @@ __device__ __forceinline__ void epilogue8(const GemmKParams& p, float* v, int co
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] += f[i];
       }
-    }
-    if (p.out_scale != 1.f) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] *= p.out_scale;
     }
     if (p.out) {
       if (p.out_dtype == CTTA_F32) {
@@ -275,11 +276,11 @@ __device__ __forceinline__ void epilogue8(const GemmKParams& p, float* v, int co
                                    : ld16(p.residual, p.res_dtype == CTTA_BF16, off);
     }
     const long long ooff = orow * p.out_ld + c;
+    x *= p.out_scale;
     if (p.accumulate) {
       x += p.out_dtype == CTTA_F32 ? reinterpret_cast<const float*>(p.out)[ooff]
                                    : ld16(p.out, p.out_dtype == CTTA_BF16, ooff);
     }
-    x *= p.out_scale;
     if (p.out) {
       if (p.out_dtype == CTTA_F32) reinterpret_cast<float*>(p.out)[ooff] = x;
       else reinterpret_cast<unsigned short*>(p.out)[ooff] = cvt16(x, p.out_dtype == CTTA_BF16);
@@ -334,7 +335,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tmem_full[s]), 1);
-      mbar_init(smem_u32(&bar_tmem_empty[s]), p.epi_tma ? kEpiWarps : 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&bar_tmem_empty[s]), p.epi_tma ? 4 * p.epi_groups : 4);  // one arrive per epilogue warp
     }
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(smem_u32(&bar_ring_full[s]), 1);
@@ -523,10 +524,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t full = smem_u32(&bar_ring_full[slot]);
             if (k < p.ring_in) {
               mbar_arrive_expect_tx(full, kRingSlotBytes);
-              // input 0 = residual (if any), then the previous contents of out (accumulate);
-              // one {32 cols x 32 rows} box per epilogue warp (the same box shape the stores use)
-              const bool is_res = (k == 0 && p.residual != nullptr);
-              const void* map = is_res ? static_cast<const void*>(&tmap_res) : static_cast<const void*>(&tmap_out);
+              // the fp32 residual tile: one {32 cols x 32 rows} box per epilogue warp (the box shape the stores use)
+              const void* map = static_cast<const void*>(&tmap_res);
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq) {
                 const int wr = qq * 32;
@@ -613,7 +612,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
    }
-  } else {
+  } else if (warp < kEpiWarp0 + 4 * p.epi_groups) {
     // ------------------------------------------------------------------ epilogue warps, TMA-staged
     // thread = accumulator row.  Two warps per TMEM lane quarter (group 0 / 1) take alternate 32-column chunks.
     // Per chunk: TMEM -> registers, + bias (smem broadcast) + rowadd, act, + residual / previous out (ring slot,
@@ -631,7 +630,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     const int q = warp & 3;
     const int ew = warp - kEpiWarp0;          // 0..7, owner of staging buffers
-    const int grp = ew >> 2;                  // chunk parity handled by this warp
+    const int grp = ew >> 2;                  // chunk phase handled by this warp
+    const int ngrp = p.epi_groups;
     const int lr = q * 32 + lane;             // row inside the tile
     const int n_chunks = p.block_n / kChunkCols;
     const int tot_chunks = n_chunks * p.sub_tiles;
@@ -672,17 +672,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       // bias of this tile -> shared memory (double buffered by tile parity)
       float* bs = bias_s + (it & 1) * 256;
-      for (int i = et; i < p.block_n; i += kEpiWarps * 32) {
+      for (int i = et; i < p.block_n; i += ngrp * 128) {
         const int c = tc.n0 + i;
         bs[i] = (p.bias != nullptr && c < p.N) ? p.bias[c] : 0.f;
       }
-      named_barrier_sync(1, kEpiWarps * 32);
+      named_barrier_sync(1, ngrp * 128);
 
       mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
       const long long chunk_base = static_cast<long long>(it) * tot_chunks;
-      const int last_cc = ((tot_chunks - 1 - grp) / 2) * 2 + grp;  // last chunk of this group (may be < 0 .. handled)
+      const int last_cc = ((tot_chunks - 1 - grp) / ngrp) * ngrp + grp;  // last chunk of this group
       if (grp >= tot_chunks) {
         // nothing to read from this accumulator stage
         __syncwarp();
@@ -690,7 +690,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       int sub = 0, ch = grp;
       while (ch >= n_chunks) { ch -= n_chunks; ++sub; }
-      for (int cc = grp; cc < tot_chunks; cc += 2, ++my_ctr) {
+      for (int cc = grp; cc < tot_chunks; cc += ngrp, ++my_ctr) {
         const int c0 = ch * kChunkCols;
         const int col = tc.n0 + c0;
         const int st_row = st_row0 + sub * kBlockM;
@@ -822,26 +822,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (out_f32) tma_store_3d(&tmap_out, ring_base + first_slot * kRingSlotBytes + wrow * 128, col, st_row, st_img);
+            if (out_f32) {
+              const uint32_t src = ring_base + first_slot * kRingSlotBytes + wrow * 128;
+              if (p.accumulate) tma_reduce_add_3d(&tmap_out, src, col, st_row, st_img);  // out += tile
+              else tma_store_3d(&tmap_out, src, col, st_row, st_img);
+            }
             if (out_16) tma_store_3d(&tmap_out, st16, col, st_row, st_img);
             if (has_out2) tma_store_3d(&tmap_out2, st16, col, st_row, st_img);
             tma_store_commit();
-            if (ring_in > 1) {
-              // two fp32 inputs per chunk (residual + accumulate): the ring is too shallow to keep a slot pending,
-              // so wait for this store's shared-memory reads and release the slot immediately
-              tma_store_wait_read<0>();
-              if (pending_slot >= 0) mbar_arrive(smem_u32(&bar_ring_empty[pending_slot]));
-              if (out_f32) mbar_arrive(smem_u32(&bar_ring_empty[first_slot]));
-            } else {
-              tma_store_wait_read<1>();  // everything but the group just committed has finished reading smem
-              if (pending_slot >= 0) mbar_arrive(smem_u32(&bar_ring_empty[pending_slot]));
-            }
+            tma_store_wait_read<1>();  // everything but the group just committed has finished reading smem
+            if (pending_slot >= 0) mbar_arrive(smem_u32(&bar_ring_empty[pending_slot]));
           }
-          pending_slot = (out_f32 && ring_in <= 1) ? first_slot : -1;
+          pending_slot = out_f32 ? first_slot : -1;
           __syncwarp();
         }
-        // advance (sub, ch) by two chunks
-        ch += 2;
+        // advance (sub, ch) to this group's next chunk
+        ch += ngrp;
         while (ch >= n_chunks) { ch -= n_chunks; ++sub; }
       }
     }
@@ -935,7 +931,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   if (d->act == CTTA_ACT_GEGLU)
     CTTA_REQUIRE(d->n % 8 == 0 && !d->residual && !d->accumulate && !d->out2 && !d->rowadd && d->out,
                  "ctta_gemm: GEGLU epilogue supports bias only and needs n %% 8 == 0");
-  if (d->accumulate) CTTA_REQUIRE(d->out != nullptr, "ctta_gemm: accumulate needs out");
+  if (d->accumulate) CTTA_REQUIRE(d->out != nullptr && d->out2 == nullptr, "ctta_gemm: accumulate needs out and excludes out2");
   if (d->rowadd) CTTA_REQUIRE(d->rowadd_rows >= 1, "ctta_gemm: rowadd_rows must be >= 1");
 
   GemmKParams p{};
@@ -1110,6 +1106,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   }
   p.out_rows_tile_img = rows_tile_img;
   p.epi_tma = tma_ok ? 1 : 0;
+  p.epi_groups = 1;
   // M super-tiles for narrow N (see GemmKParams::sub_tiles)
   p.sub_tiles = 1;
   if (tma_ok && d->a_mode != CTTA_A_CONV2D && !d->rowadd && block_n <= 128 && getenv("CTTA_NO_SUPERTILE") == nullptr) {
@@ -1157,31 +1154,38 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
                              d->out_rows_per_img, d->n_img, kChunkCols, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
-    p.ring_in = (d->residual ? 1 : 0) + (d->accumulate ? 1 : 0);
+    p.ring_in = d->residual ? 1 : 0;
     const bool out_f32 = d->out && d->out_dtype == CTTA_F32;
     const bool use_ring = out_f32 || p.ring_in > 0;
     p.ring_per_chunk = use_ring ? (p.ring_in > 1 ? p.ring_in : 1) : 0;
-    st16_bytes = ((d->out && !out_f32) || d->out2) ? kEpiWarps * 2 * kStage16Bytes : 0;
+    const bool need16 = (d->out && !out_f32) || d->out2;
     bias_bytes = kBiasBytes;
-    const int budget = kSmemBudget - p.tiles_off - st16_bytes - bias_bytes;
-    int stages = 0, ring = 0;
-    if (!use_ring) {
-      stages = budget / p.stage_bytes;
-    } else {
-      // ring depth hides the residual-load latency, mainloop stages hide the operand-load latency: prefer a ring
-      // of 4 (>= 2 chunks in flight per input), then 3, then the minimum, as long as >= 3 mainloop stages remain
-      // a slot that is also the TMA-store source is released one chunk late by each of the two warp groups
-      const int need = ((out_f32 && p.ring_in < 2) ? 3 : 2) * p.ring_per_chunk;
-      const int prefs[3] = {need > 4 ? need : 4, need > 3 ? need : 3, need};
-      for (int i = 0; i < 3 && stages == 0; ++i) {
-        const int st = (budget - prefs[i] * kRingSlotBytes) / p.stage_bytes;
-        if (st >= 3 || (i == 2 && st >= 2)) {
-          stages = st;
-          ring = prefs[i];
+    int stages = 0, ring = 0, groups = 2;
+    // two groups of epilogue warps double the epilogue throughput but cost staging memory and ring depth; fall
+    // back to one group when that would leave fewer than 3 mainloop stages (wide, MMA-bound tiles)
+    for (groups = 2; groups >= 1 && stages == 0; --groups) {
+      st16_bytes = need16 ? groups * 4 * 2 * kStage16Bytes : 0;
+      const int budget = kSmemBudget - p.tiles_off - st16_bytes - bias_bytes;
+      if (!use_ring) {
+        const int st = budget / p.stage_bytes;
+        if (st >= 3 || groups == 1) stages = st;
+      } else {
+        // a slot that is also a TMA-store source is released one chunk late by each warp group
+        const int need = (out_f32 ? groups + 1 : 2) * p.ring_per_chunk;
+        const int prefs[3] = {need > 4 ? need : 4, need > 3 ? need : 3, need};
+        for (int i = 0; i < 3 && stages == 0; ++i) {
+          const int st = (budget - prefs[i] * kRingSlotBytes) / p.stage_bytes;
+          if (st >= 3 || (groups == 1 && i == 2 && st >= 2)) {
+            stages = st;
+            ring = prefs[i];
+          }
         }
       }
-      CTTA_REQUIRE(stages > 0, "ctta_gemm: shared-memory plan failed (block_n=%d)", block_n);
+      if (stages > 0) break;
     }
+    CTTA_REQUIRE(stages > 0, "ctta_gemm: shared-memory plan failed (block_n=%d)", block_n);
+    p.epi_groups = groups;
+    const int budget = kSmemBudget - p.tiles_off - st16_bytes - bias_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     CTTA_REQUIRE(stages >= 2, "ctta_gemm: shared-memory plan failed (block_n=%d, stages=%d)", block_n, stages);
     if (use_ring) {
@@ -1217,8 +1221,6 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   static const Variant variants[] = {
       {N_, 0, 0, 0, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 0, 0, 0, 1, L_>>},  // conv -> lrelu'ed 16-bit operand
       {N_, 0, 1, 1, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 1, 1, 0, 1, L_>>},  // + residual, fp32 stream + operand
-      {N_, 0, 2, 1, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 2, 1, 0, 1, L_>>},  // + accumulate
-      {N_, 0, 2, 1, 0, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 2, 1, 0, 0, N_>>},
       {N_, 0, 0, 1, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 0, 1, 0, 1, L_>>},  // transposed conv
       {N_, 0, 1, 1, 0, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 1, 1, 0, 0, N_>>},  // fp32 out + residual
       {N_, 1, 0, 1, 0, 0, N_, gemm_tc_kernel<EpiCfg<N_, 1, 0, 1, 0, 0, N_>>},  // fp32 out + time embedding

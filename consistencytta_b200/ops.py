@@ -347,6 +347,14 @@ def wave_to_int16(wav, minmax=None, out=None):
     return out, minmax
 
 
+def lrelu_cast(x, slope, out=None):
+    """fp32 tensor -> 16-bit leaky_relu(x, slope)."""
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=OPERAND_DTYPE)
+    check(lib().ctta_lrelu_cast(_ptr(x), x.numel(), slope, _ptr(out), _DT[out.dtype], _stream()))
+    return out
+
+
 def cfg_mix(x, s, out=None):
     half = x.shape[0] // 2
     if out is None:

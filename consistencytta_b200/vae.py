@@ -89,10 +89,10 @@ class Generator(PackedModule):
                                    act2=ACT_LRELU, act2_slope=0.1)
                         res, a16 = dst, r16
                     else:
-                        fin = j == nk - 1
+                        # MRF: x = (sum_j resblock_j(x)) / 3 (models.py:108-112) accumulated in fp32 by the TMA unit
                         ops.conv1d(tmp16, pk["rb.%d.c2.%d" % (n, m)], out=xs, residual=res, accumulate=j > 0,
-                                   out_scale=(1.0 / nk) if fin else 1.0, out2=nxt16 if fin else None,
-                                   act2=ACT_LRELU, act2_slope=0.01 if last else 0.1)
+                                   out_scale=1.0 / nk)
+            ops.lrelu_cast(xs, 0.01 if last else 0.1, out=nxt16)  # models.py:104 / :113 (default slope)
             cur16 = nxt16
         wav = torch.empty(b, t, 1, device=dev, dtype=torch.float32)
         ops.conv1d(cur16, pk["conv_post"], out=wav, act=ACT_TANH)  # models.py:113-115

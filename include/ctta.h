@@ -57,8 +57,8 @@ long long ctta_launch_count(void);
  * Implicit-GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators, persistent, warp-specialised):
  *     acc[m, n] = sum_{tap j} sum_{c < C} A(m shifted by tap j, c) * W[n, j * c_pad + c]
  *     v   = act(acc + bias[n] + rowadd[img(m), n])
- *     v   = (v + residual[orow(m), n] + (accumulate ? out[orow(m), n] : 0)) * out_scale
- *     out[orow(m), n] = v ;   out2[orow(m), n] = f16/bf16( act2(v) )      (out2 optional)
+ *     v   = (v + residual[orow(m), n]) * out_scale
+ *     out[orow(m), n] = v (+ out[orow(m), n] if accumulate) ;   out2[orow(m), n] = f16/bf16( act2(v) )   (optional)
  * Replaces, in the reference: F.conv2d 3x3/1x1 (diffusers/models/resnet.py:570,590,593,157;
  * unet_2d_condition_guided.py:863,940; audioldm/variational_autoencoder/modules.py:56,159,167,173,207-209,228,
  * 658,680; autoencoder.py:99), F.linear (attention_processor.py:1110-1135; transformer_2d.py:267,295;
@@ -94,7 +94,7 @@ typedef struct {
   const void* residual;   /* [*, res_ld] or NULL */
   int32_t res_dtype;      /* CTTA_F32 / CTTA_F16 / CTTA_BF16 */
   int32_t res_ld;
-  int32_t accumulate;     /* add the previous contents of out */
+  int32_t accumulate;     /* out += v (TMA reduce-add into global memory); excludes out2 */
   float out_scale;
   void* out;              /* may be NULL when only out2 is wanted */
   int32_t out_dtype;
@@ -174,6 +174,10 @@ int ctta_small_linear(const float* x, int32_t m, int32_t k, const float* wgt, co
  * truncate toward zero to int16 (numpy astype semantics incl. wrap-around). minmax = float[2] scratch. */
 int ctta_wave_minmax(const float* wav, int64_t numel, float* minmax, void* stream);
 int ctta_wave_to_int16(const float* wav, int64_t numel, const float* minmax, int16_t* out, void* stream);
+
+/* y = 16-bit(leaky_relu(x, slope)) elementwise: operand of the next up-sampling stage after the MRF sum
+ * (audioldm/hifigan/models.py:104,112-113). */
+int ctta_lrelu_cast(const float* x, int64_t numel, float slope, void* y, int32_t y_dtype, void* stream);
 
 /* (1 - s) * uncond + s * cond on the two batch halves (models/audio_consistency_model.py:453-456). */
 int ctta_cfg_mix(const float* x, int64_t half_numel, float s, float* y, void* stream);

@@ -109,13 +109,21 @@ def test_conv1d(k, dil, c, t):
     out = xs.clone()
     out2 = torch.empty(bsz, t, c, device=DEV, dtype=DT)
     res = torch.randn(bsz, t, c, device=DEV)
-    ops.conv1d(a, pw, out=out, residual=res, accumulate=True, out_scale=1 / 3, out2=out2, act2=ops.ACT_LRELU,
-               act2_slope=0.1)
     # a is rounded to fp16 after lrelu; recompute the reference from it
-    ref = F.conv1d(a.float().permute(0, 2, 1), wt, b, dilation=dil, padding=(k * dil - dil) // 2)
-    full = (ref.permute(0, 2, 1) + res + xs) / 3
-    assert rel(out, full) < 2e-5
-    assert rel(out2, F.leaky_relu(full, 0.1)) < 1e-3
+    ref = F.conv1d(a.float().permute(0, 2, 1), wt, b, dilation=dil, padding=(k * dil - dil) // 2).permute(0, 2, 1)
+    # residual + second (activated 16-bit) output
+    o1 = torch.empty(bsz, t, c, device=DEV)
+    ops.conv1d(a, pw, out=o1, residual=res, out2=out2, act2=ops.ACT_LRELU, act2_slope=0.1)
+    assert rel(o1, ref + res) < 2e-5
+    assert rel(out2, F.leaky_relu(ref + res, 0.1)) < 1e-3
+    # accumulate: out += (conv + residual) * scale
+    ops.conv1d(a, pw, out=out, residual=res, accumulate=True, out_scale=1 / 3)
+    assert rel(out, xs + (ref + res) / 3) < 2e-5
+    # operand-only output
+    ops.conv1d(a, pw, out2=out2, act2=ops.ACT_LRELU, act2_slope=0.1)
+    assert rel(out2, F.leaky_relu(ref, 0.1)) < 1e-3
+    y16 = ops.lrelu_cast(out, 0.01)
+    assert rel(y16, F.leaky_relu(out, 0.01)) < 1e-3
 
 
 @pytest.mark.parametrize("k,s,cin,cout,t", [(16, 5, 128, 64, 50), (16, 4, 64, 32, 131), (8, 2, 64, 64, 200),
