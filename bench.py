@@ -152,6 +152,7 @@ def main():
     import torch
     import torch.distributed as dist
     from consistencytta_b200 import SingleStepEngine, build_random_init_models, ops, weights
+    from consistencytta_b200.distributed import gather_waveforms
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -173,7 +174,6 @@ def main():
     kvlen_h = mask.sum(1).to(torch.int32).pin_memory()
     out_h = torch.empty(B, CLIP_SAMPLES, dtype=torch.int16).pin_memory()
     lat_h = torch.empty(B, 8, 256, 16, dtype=torch.float32).pin_memory()
-    gathered = [torch.empty(B, CLIP_SAMPLES, dtype=torch.int16, device=dev) for _ in range(world)] if world > 1 else None
 
     def sync_all():
         if world > 1:
@@ -209,7 +209,7 @@ def main():
         if stages == "all":
             out_h.copy_(r["int16"][:, :CLIP_SAMPLES], non_blocking=True)
             if world > 1:  # NCCL is used only to gather the waveforms for output (north_star)
-                dist.all_gather(gathered, r["int16"][:, :CLIP_SAMPLES].contiguous())
+                gather_waveforms(r["int16"][:, :CLIP_SAMPLES], B * world)
         else:
             lat_h.copy_(r["latent"], non_blocking=True)
     for _ in range(2):
