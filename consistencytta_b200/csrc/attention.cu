@@ -296,6 +296,12 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   }
 }
 
+// attention_tc.cu: tcgen05 kernel for long key sequences; returns 1 when the problem is not eligible
+int attention_tc_launch(const void* q, const void* k, const void* v, void* o, int dtype, int batch, int heads, int lq,
+                        int lk, long long q_bs, long long q_ls, long long k_bs, long long k_ls, long long v_bs,
+                        long long v_ls, long long o_bs, long long o_ls, const int* kv_len, float scale,
+                        cudaStream_t stream);
+
 }  // namespace ctta
 
 using namespace ctta;
@@ -316,6 +322,13 @@ extern "C" int ctta_attention(const void* q, const void* k, const void* v, void*
                    (reinterpret_cast<uintptr_t>(o) & 3) == 0,
                "attention: tensors must be 16-byte aligned");
   CTTA_REQUIRE(batch <= 65535 && heads <= 65535, "attention: batch / heads exceed grid limits");
+  {
+    // self-attention sized problems run on the tcgen05 kernel; short key sequences (text cross-attention, the
+    // 64-token mid block) stay on the mma.sync kernel below, where a 128-key tile would be mostly padding
+    const int rc = attention_tc_launch(q, k, v, o, dtype, batch, heads, lq, lk, q_bs, q_ls, k_bs, k_ls, v_bs, v_ls, o_bs,
+                                       o_ls, kv_len, scale, stream);
+    if (rc <= 0) return rc;
+  }
   dim3 grid((lq + kBr - 1) / kBr, heads, batch);
   const float scale_log2 = scale * 1.4426950408889634f;
   if (dtype == CTTA_BF16) {

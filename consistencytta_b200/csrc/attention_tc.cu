@@ -1,0 +1,376 @@
+// Fused flash-style self-attention on tcgen05 tensor cores for head_dim 64 (the UNet's 51-wide heads padded to 64).
+//
+// One CTA = one (batch, head) and 256 query rows = two independent 128-row tiles that share every K/V tile.
+// 10 warps: warp 0 = TMA loader (Q once, K/V through a 3-stage ring), warp 1 = single-thread tcgen05.mma issuer,
+// warps 2..5 / 6..9 = softmax warp groups of query tile 0 / 1 (thread == query row, so the row max / row sum need no
+// shuffles).  Per key tile of 128:
+//     S_t   = Q_t K^T            UMMA 128x128x64, fp32 in TMEM (S_t: 128 columns)
+//     P_t   = exp2(c S_t - c m)  softmax warps: tcgen05.ld -> registers -> 16-bit P into swizzled shared memory
+//     O_t  += P_t V              UMMA 128x64x128, V is the MN-major B operand exactly as TMA lands it ([keys, d])
+// The issuer runs QK^T of key tile j+1 as soon as the softmax warps have pulled S(j) into registers, so the tensor
+// core works under the exponentials.  The running max is updated lazily: O_t (in TMEM) is only rescaled when some row
+// of the warp saw its max grow by more than 2^8, which keeps P <= 256 and the result exact (the same stale max is
+// used for the row sum).  Keys >= kv_len[b] get -inf, i.e. the reference's additive -10000 mask bias.
+//
+// Reference call site: F.scaled_dot_product_attention, diffusers/models/attention_processor.py:1127-1129.
+#include <cuda.h>
+#include <cstdlib>
+#include "ctta_internal.h"
+#include "ctta_ptx.cuh"
+
+namespace ctta {
+
+int make_tmap_ex(CUtensorMap* m, int dtype, CUtensorMapSwizzle swz, const void* base, int rank, const cuuint64_t* dims,
+                 const cuuint64_t* strides_bytes, const cuuint32_t* box);
+
+namespace atc {
+
+constexpr int kTile = 128;                   // query rows per tile == keys per tile
+constexpr int kD = 64;
+constexpr int kTileBytes = kTile * kD * 2;   // 16 KiB: one [128 x 64] 16-bit operand tile (rows of 128 B, SW128)
+constexpr int kStages = 3;
+constexpr int kThreads = 320;
+constexpr int kSmemQ = 0;
+constexpr int kSmemKV = kSmemQ + 2 * kTileBytes;             // K then V per stage
+constexpr int kSmemP = kSmemKV + kStages * 2 * kTileBytes;   // per query tile: two [128 x 64] K-major halves
+constexpr int kSmemTotal = kSmemP + 2 * 2 * kTileBytes;      // 192 KiB
+constexpr int kTmemCols = 512;
+constexpr int kColS = 0, kColO = 256;        // S_t at 128 t, O_t at 256 + 64 t
+constexpr float kLazyThreshold = 8.f;        // log2 units
+
+struct Params {
+  int lq, lk, heads;
+  const int* kv_len;
+  float scale_log2;
+  unsigned short* o;
+  long long o_bs, o_ls;
+  int is_bf16;
+};
+
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+      "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+      "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// MN-major B operand (V as [keys, d] rows of 128 B, SW128): 8-key groups are 1024 B apart (stride byte offset);
+// the leading byte offset (between 64-wide d blocks) is unused for N = 64.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_p(float a, float b, int is_bf16) {
+  uint32_t r;
+  if (is_bf16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q_full;
+  __shared__ __align__(8) uint64_t bar_kv_full[kStages], bar_kv_empty[kStages];
+  __shared__ __align__(8) uint64_t bar_s_full[2], bar_s_free[2], bar_p_full[2], bar_pv_done[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * 2 * kTile;
+
+  int kvl = p.kv_len ? p.kv_len[b] : p.lk;
+  kvl = max(1, min(kvl, p.lk));
+  const int n_tiles = (kvl + kTile - 1) / kTile;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar_q_full), 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&bar_kv_full[s]), 1);
+      mbar_init(smem_u32(&bar_kv_empty[s]), 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&bar_s_full[t]), 1);
+      mbar_init(smem_u32(&bar_s_free[t]), 4);   // one arrive per softmax warp
+      mbar_init(smem_u32(&bar_p_full[t]), 4);
+      mbar_init(smem_u32(&bar_pv_done[t]), 1);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA loader
+    if (elect_one_sync()) {
+      const uint32_t qf = smem_u32(&bar_q_full);
+      mbar_arrive_expect_tx(qf, 2 * kTileBytes);
+      tma_load_4d(base + kSmemQ, &tmap_q, qf, 0, head, q0, b);
+      tma_load_4d(base + kSmemQ + kTileBytes, &tmap_q, qf, 0, head, q0 + kTile, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(smem_u32(&bar_kv_empty[stage]), phase ^ 1u);
+        const uint32_t full = smem_u32(&bar_kv_full[stage]);
+        mbar_arrive_expect_tx(full, 2 * kTileBytes);
+        const uint32_t dst = base + kSmemKV + stage * 2 * kTileBytes;
+        tma_load_4d(dst, &tmap_k, full, 0, head, j * kTile, b);
+        tma_load_4d(dst + kTileBytes, &tmap_v, full, 0, head, j * kTile, b);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one_sync()) {
+      const uint32_t idesc_qk = umma_idesc(kTile, kTile, p.is_bf16);                 // 128 x 128, A and B K-major
+      const uint32_t idesc_pv = umma_idesc(kTile, kD, p.is_bf16) | (1u << 16);       // 128 x 64, B (= V) MN-major
+      mbar_wait(smem_u32(&bar_q_full), 0);
+      mbar_wait(smem_u32(&bar_kv_full[0]), 0);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t a = base + kSmemQ + t * kTileBytes, bk = base + kSmemKV;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16(tmem_base + kColS + t * kTile, umma_desc_sw128(a + kk * 32), umma_desc_sw128(bk + kk * 32), idesc_qk,
+                   kk != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&bar_s_full[t]));
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t par = static_cast<uint32_t>(j & 1);
+        const int stage = j % kStages;
+        if (j + 1 < n_tiles) {
+          const int nstage = (j + 1) % kStages;
+          mbar_wait(smem_u32(&bar_kv_full[nstage]), static_cast<uint32_t>(((j + 1) / kStages) & 1));
+          const uint32_t bk = base + kSmemKV + nstage * 2 * kTileBytes;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(smem_u32(&bar_s_free[t]), par);   // softmax has S_t(j) in registers
+            tc_fence_after();
+            const uint32_t a = base + kSmemQ + t * kTileBytes;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(tmem_base + kColS + t * kTile, umma_desc_sw128(a + kk * 32), umma_desc_sw128(bk + kk * 32),
+                       idesc_qk, kk != 0 ? 1u : 0u);
+            umma_commit(smem_u32(&bar_s_full[t]));
+          }
+        }
+        const uint32_t bv = base + kSmemKV + stage * 2 * kTileBytes + kTileBytes;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(smem_u32(&bar_p_full[t]), par);     // P_t(j) is in shared memory, O_t rescaled if needed
+          tc_fence_after();
+          const uint32_t pa = base + kSmemP + t * 2 * kTileBytes;
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            umma_f16(tmem_base + kColO + t * kD, umma_desc_sw128(pa + (s >> 2) * kTileBytes + (s & 3) * 32),
+                     umma_desc_sw128_mn(bv + s * 2048), idesc_pv, (j | s) != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&bar_pv_done[t]));
+        }
+        umma_commit(smem_u32(&bar_kv_empty[stage]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps (thread == query row)
+    const int t = (warp - 2) >> 2;                  // query tile of this warp group
+    const int q = warp & 3;                         // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;                  // row inside the tile
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_addr + kColS + t * kTile;
+    const uint32_t o_addr = tmem_base + lane_addr + kColO + t * kD;
+    const uint32_t p_row = base + kSmemP + t * 2 * kTileBytes + row * 128;
+    const int sw = row & 7;
+    const float c = p.scale_log2;
+    float m_used = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t par = static_cast<uint32_t>(j & 1);
+      mbar_wait(smem_u32(&bar_s_full[t]), par);
+      tc_fence_after();
+      uint32_t u[128];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) tmem_ld_x32(s_addr + ch * 32, u + ch * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_s_free[t]));
+      float* s = reinterpret_cast<float*>(u);
+      const int valid = kvl - j * kTile;            // keys of this tile below kv_len
+      if (valid < kTile) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= valid) s[i] = -INFINITY;
+      }
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int i = 4; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, s[i]);
+        mx1 = fmaxf(mx1, s[i + 1]);
+        mx2 = fmaxf(mx2, s[i + 2]);
+        mx3 = fmaxf(mx3, s[i + 3]);
+      }
+      const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
+      bool waited_pv = false;
+      if (j == 0) {
+        m_used = m_new;
+      } else {
+        const bool need = (m_new - m_used) * c > kLazyThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // rescale O_t (and the row sum) to the new max; needs PV(j-1) to have landed in TMEM
+          mbar_wait(smem_u32(&bar_pv_done[t]), par ^ 1u);
+          waited_pv = true;
+          tc_fence_after();
+          const float alpha = fast_exp2((m_used - m_new) * c);
+          m_used = m_new;
+          l_sum *= alpha;
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tmem_ld_x32(o_addr + hh * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(o_addr + hh * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float mc = m_used * c;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        s[i] = fast_exp2(fmaf(s[i], c, -mc));
+        s[i + 1] = fast_exp2(fmaf(s[i + 1], c, -mc));
+        s[i + 2] = fast_exp2(fmaf(s[i + 2], c, -mc));
+        s[i + 3] = fast_exp2(fmaf(s[i + 3], c, -mc));
+        l0 += s[i];
+        l1 += s[i + 1];
+        l2 += s[i + 2];
+        l3 += s[i + 3];
+      }
+      l_sum += (l0 + l1) + (l2 + l3);
+      if (j > 0 && !waited_pv) mbar_wait(smem_u32(&bar_pv_done[t]), par ^ 1u);   // PV(j-1) no longer reads P_t
+#pragma unroll
+      for (int ck = 0; ck < 16; ++ck) {
+        const uint32_t w0 = pack_p(s[8 * ck + 0], s[8 * ck + 1], p.is_bf16);
+        const uint32_t w1 = pack_p(s[8 * ck + 2], s[8 * ck + 3], p.is_bf16);
+        const uint32_t w2 = pack_p(s[8 * ck + 4], s[8 * ck + 5], p.is_bf16);
+        const uint32_t w3 = pack_p(s[8 * ck + 6], s[8 * ck + 7], p.is_bf16);
+        const uint32_t dst = p_row + (ck >> 3) * kTileBytes + (((ck & 7) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+      }
+      fence_proxy_async();   // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
+      tc_fence_before();     // orders the O rescale (tcgen05.st) before the arrive
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_p_full[t]));
+    }
+    // ---- epilogue: O_t / l -> 16-bit, this thread's row
+    mbar_wait(smem_u32(&bar_pv_done[t]), static_cast<uint32_t>((n_tiles - 1) & 1));
+    tc_fence_after();
+    uint32_t o[64];
+    tmem_ld_x32(o_addr, o);
+    tmem_ld_x32(o_addr + 32, o + 32);
+    tmem_ld_wait();
+    const float inv = 1.f / l_sum;
+    const int grow = q0 + t * kTile + row;
+    if (grow < p.lq) {
+      unsigned short* dst = p.o + static_cast<long long>(b) * p.o_bs + static_cast<long long>(grow) * p.o_ls + head * kD;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 w;
+        w.x = pack_p(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv, p.is_bf16);
+        w.y = pack_p(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv, p.is_bf16);
+        w.z = pack_p(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv, p.is_bf16);
+        w.w = pack_p(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv, p.is_bf16);
+        *reinterpret_cast<uint4*>(dst + 8 * g) = w;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+static int make_qkv_tmap(CUtensorMap* m, int dtype, const void* ptr, int heads, int len, int batch, long long ls,
+                         long long bs) {
+  cuuint64_t dims[4] = {(cuuint64_t)kD, (cuuint64_t)heads, (cuuint64_t)len, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {(cuuint64_t)kD * 2, (cuuint64_t)ls * 2, (cuuint64_t)bs * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kD, 1, (cuuint32_t)kTile, 1};
+  return make_tmap_ex(m, dtype, CU_TENSOR_MAP_SWIZZLE_128B, ptr, 4, dims, strides, box);
+}
+
+}  // namespace atc
+
+// Launches the tcgen05 kernel; returns 1 if the problem is not eligible (caller falls back to the mma.sync kernel
+// for short key sequences), 0 on success, < 0 on error.
+int attention_tc_launch(const void* q, const void* k, const void* v, void* o, int dtype, int batch, int heads, int lq,
+                        int lk, long long q_bs, long long q_ls, long long k_bs, long long k_ls, long long v_bs,
+                        long long v_ls, long long o_bs, long long o_ls, const int* kv_len, float scale,
+                        cudaStream_t stream) {
+  using namespace atc;
+  if (lq < kTile || lk < kTile || getenv("CTTA_ATTN_LEGACY") != nullptr) return 1;
+  if (o_ls % 8 != 0 || o_bs % 8 != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0) return 1;
+  CUtensorMap tq, tk, tv;
+  int rc = make_qkv_tmap(&tq, dtype, q, heads, lq, batch, q_ls, q_bs);
+  if (rc) return rc;
+  rc = make_qkv_tmap(&tk, dtype, k, heads, lk, batch, k_ls, k_bs);
+  if (rc) return rc;
+  rc = make_qkv_tmap(&tv, dtype, v, heads, lk, batch, v_ls, v_bs);
+  if (rc) return rc;
+  Params p{};
+  p.lq = lq;
+  p.lk = lk;
+  p.heads = heads;
+  p.kv_len = kv_len;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.o = reinterpret_cast<unsigned short*>(o);
+  p.o_bs = o_bs;
+  p.o_ls = o_ls;
+  p.is_bf16 = dtype == CTTA_BF16;
+  static bool configured = false;
+  if (!configured) {
+    CTTA_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(flash_attn_tc_kernel),
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal + 1024));
+    configured = true;
+  }
+  dim3 grid((lq + 2 * kTile - 1) / (2 * kTile), heads, batch);
+  flash_attn_tc_kernel<<<grid, kThreads, kSmemTotal + 1024, stream>>>(tq, tk, tv, p);
+  CTTA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ctta

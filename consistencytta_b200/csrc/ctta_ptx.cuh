@@ -12,6 +12,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a CONVERGED warp.  Unlike `lane == 0`, ptxas knows exactly one thread is active behind this predicate,
+// so warp-uniform instructions (UTCHMMA, UTMALDG, UTMASTG, UTCBAR) are issued straight instead of inside an
+// ELECT / BRA.U.ANY serialisation loop (about 12 extra SASS instructions per tcgen05.mma otherwise).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -366,7 +366,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t stages_base = tiles_base + static_cast<uint32_t>(p.tiles_off);
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane)
-    if (lane == 0 && p.halo) {
+    const bool leader = elect_one_sync();
+    if (leader && p.halo) {
       // resident weights: one {64 x block_n} box per tap, loaded once per CTA
       const uint32_t wbar = smem_u32(&bar_weights);
       mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(p.w_bytes));
@@ -389,7 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
-    } else if (lane == 0) {
+    } else if (leader) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = static_cast<uint32_t>(p.stage_bytes);
@@ -425,7 +426,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0 && p.halo) {
+    const bool leader = elect_one_sync();
+    if (leader && p.halo) {
       const uint32_t idesc = umma_idesc(kBlockM, p.block_n, p.is_bf16);
       mbar_wait(smem_u32(&bar_weights), 0);
       int stage = 0;
@@ -458,7 +460,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         umma_commit(smem_u32(&bar_tmem_full[acc]));
       }
-    } else if (lane == 0) {
+    } else if (leader) {
       const uint32_t idesc = umma_idesc(kBlockM, p.block_n, p.is_bf16);
       int stage = 0;
       uint32_t phase = 0;
@@ -498,7 +500,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ------------------------------------------------------------------ epilogue loader (one lane)
     // Streams the fp32 residual / previous-output tiles of every chunk into the ring, running ahead of the
     // epilogue math by up to ring_slots chunks.  With no inputs it only hands out free slots (pure staging).
-    if (lane == 0 && p.epi_tma && p.ring_slots > 0) {
+    if (elect_one_sync() && p.epi_tma && p.ring_slots > 0) {
       const int n_chunks = p.block_n / kChunkCols;
       const uint32_t ring_base = tiles_base + static_cast<uint32_t>(p.ring_off);
       int slot = 0;
@@ -628,6 +630,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool generic = Cfg::kAct < 0;       // only the generic instance supports bf16 outputs
     const int ring_per_chunk = (out_f32 || ring_in > 0) ? (ring_in > 1 ? ring_in : 1) : 0;
 
+    const bool leader = elect_one_sync();     // the lane that owns this warp's bulk-store groups
     const int q = warp & 3;
     const int ew = warp - kEpiWarp0;          // 0..7, owner of staging buffers
     const int grp = ew >> 2;                  // chunk phase handled by this warp
@@ -742,7 +745,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (leader) {
             tma_store_3d(&tmap_out, st16, col >> 1, st_row, st_img);
             tma_store_commit();
             tma_store_wait_read<1>();
@@ -821,7 +824,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (leader) {
             if (out_f32) {
               const uint32_t src = ring_base + first_slot * kRingSlotBytes + wrow * 128;
               if (p.accumulate) tma_reduce_add_3d(&tmap_out, src, col, st_row, st_img);  // out += tile
@@ -841,7 +844,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         while (ch >= n_chunks) { ch -= n_chunks; ++sub; }
       }
     }
-    if (lane == 0) tma_store_wait_all();  // global writes complete before the CTA exits
+    if (leader) tma_store_wait_all();  // global writes complete before the CTA exits
   }
 
   tc_fence_before();
@@ -870,7 +873,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_tmap_ex(CUtensorMap* m, int dtype, CUtensorMapSwizzle swz, const void* base, int rank,
+int make_tmap_ex(CUtensorMap* m, int dtype, CUtensorMapSwizzle swz, const void* base, int rank,
                         const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(CTTA_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");

@@ -84,7 +84,61 @@ __global__ void __launch_bounds__(256) gn_moments_kernel(const void* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------- GN apply
-// One thread per (pixel, 4-channel vector). grid (blocks, n_img).
+// One item = (pixel, 8-channel vector): 32 B (fp32) or 16 B (16-bit) in, 16 B out.  Each thread keeps kGnItems items in
+// flight (all loads issued before any use) so a resident SM has >= 100 KB of reads outstanding; 32-bit index math.
+// grid (blocks, n_img).
+constexpr int kGnItems = 2;
+
+struct Vec8 {
+  float v[8];
+};
+__device__ __forceinline__ Vec8 load8(const void* base, int dtype, long long elem_off) {
+  Vec8 r;
+  if (dtype == CTTA_F32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off) + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(base) + elem_off));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (dtype == CTTA_BF16) {
+        r.v[2 * i] = __uint_as_float(w[i] << 16);
+        r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+      } else {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        r.v[2 * i] = t.x;
+        r.v[2 * i + 1] = t.y;
+      }
+    }
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 pack8(const Vec8& f, int dtype) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (dtype == CTTA_BF16) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f.v[2 * i], f.v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(f.v[2 * i + 1]), "f"(f.v[2 * i]));
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void store8(void* base, int dtype, long long elem_off, const Vec8& f) {
+  if (dtype == CTTA_F32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off);
+    o[0] = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
+    o[1] = make_float4(f.v[4], f.v[5], f.v[6], f.v[7]);
+  } else {
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(base) + elem_off) = pack8(f, dtype);
+  }
+}
+
 __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ x, int x_dtype, int c, int ld,
                                                        const void* __restrict__ x2, int c2, int ld2, int h, int w,
                                                        int groups, const float* __restrict__ stats,
@@ -106,45 +160,62 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
     s_rstd[threadIdx.x] = rsqrtf(var + eps);
   }
   __syncthreads();
-  const int nvec = ctot >> 2;
-  const long long total = static_cast<long long>(hw) * nvec;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(idx % nvec);
-    const int pix = static_cast<int>(idx / nvec);
-    const int ch = v << 2;
-    const bool second = ch >= c;
-    const void* src = second ? x2 : x;
-    const int sld = second ? ld2 : ld;
-    const int sch = second ? ch - c : ch;
-    float4 f = load4(src, x_dtype, (static_cast<long long>(n) * hw + pix) * sld + sch);
-    if (raw) store4(raw, y_dtype, (static_cast<long long>(n) * hw + pix) * raw_ld + ch, f);
-    if (stats) {
-      const int g = ch / cpg;
-      const float m = s_mean[g], rs = s_rstd[g];
-      const float4 ga = *reinterpret_cast<const float4*>(gamma + ch);
-      const float4 be = *reinterpret_cast<const float4*>(beta + ch);
-      f.x = (f.x - m) * rs * ga.x + be.x;
-      f.y = (f.y - m) * rs * ga.y + be.y;
-      f.z = (f.z - m) * rs * ga.z + be.z;
-      f.w = (f.w - m) * rs * ga.w + be.w;
+  const unsigned nvec = static_cast<unsigned>(ctot) >> 3;
+  const unsigned total = static_cast<unsigned>(hw) * nvec;  // < 2^31: checked on the host
+  const unsigned step = gridDim.x * blockDim.x;
+  const long long img_row0 = static_cast<long long>(n) * hw;
+  for (unsigned base = blockIdx.x * blockDim.x + threadIdx.x; base < total; base += step * kGnItems) {
+    Vec8 f[kGnItems];
+    unsigned pix[kGnItems], ch[kGnItems];
+    bool ok[kGnItems];
+#pragma unroll
+    for (int k = 0; k < kGnItems; ++k) {
+      const unsigned idx = base + k * step;
+      ok[k] = idx < total;
+      pix[k] = idx / nvec;
+      ch[k] = (idx - pix[k] * nvec) << 3;
+      if (ok[k]) {
+        const bool second = ch[k] >= static_cast<unsigned>(c);
+        f[k] = load8(second ? x2 : x, x_dtype,
+                     (img_row0 + pix[k]) * (second ? ld2 : ld) + (second ? ch[k] - c : ch[k]));
+      }
     }
-    if (act == CTTA_ACT_SILU) {
-      f.x = f.x / (1.f + __expf(-f.x));
-      f.y = f.y / (1.f + __expf(-f.y));
-      f.z = f.z / (1.f + __expf(-f.z));
-      f.w = f.w / (1.f + __expf(-f.w));
-    }
-    if (!up) {
-      store4(y, y_dtype, (static_cast<long long>(n) * hw + pix) * y_ld + ch, f);
-    } else {
-      const int ph = pix / w, pw = pix - ph * w;
-      const int w2 = 2 * w;
-      const long long o = (static_cast<long long>(n) * 4 * hw + static_cast<long long>(2 * ph) * w2 + 2 * pw);
-      store4(y, y_dtype, o * y_ld + ch, f);
-      store4(y, y_dtype, (o + 1) * y_ld + ch, f);
-      store4(y, y_dtype, (o + w2) * y_ld + ch, f);
-      store4(y, y_dtype, (o + w2 + 1) * y_ld + ch, f);
+#pragma unroll
+    for (int k = 0; k < kGnItems; ++k) {
+      if (!ok[k]) continue;
+      if (raw) store8(raw, y_dtype, (img_row0 + pix[k]) * raw_ld + ch[k], f[k]);
+      if (stats) {
+        const int g = ch[k] / cpg;  // 8 | cpg is not required: 4 | cpg, so the vector may straddle two groups
+        const int g2 = (ch[k] + 4) / cpg;
+        const float m0 = s_mean[g], r0 = s_rstd[g], m1 = s_mean[g2], r1 = s_rstd[g2];
+        const float4 ga0 = __ldg(reinterpret_cast<const float4*>(gamma + ch[k]));
+        const float4 ga1 = __ldg(reinterpret_cast<const float4*>(gamma + ch[k]) + 1);
+        const float4 be0 = __ldg(reinterpret_cast<const float4*>(beta + ch[k]));
+        const float4 be1 = __ldg(reinterpret_cast<const float4*>(beta + ch[k]) + 1);
+        f[k].v[0] = (f[k].v[0] - m0) * r0 * ga0.x + be0.x;
+        f[k].v[1] = (f[k].v[1] - m0) * r0 * ga0.y + be0.y;
+        f[k].v[2] = (f[k].v[2] - m0) * r0 * ga0.z + be0.z;
+        f[k].v[3] = (f[k].v[3] - m0) * r0 * ga0.w + be0.w;
+        f[k].v[4] = (f[k].v[4] - m1) * r1 * ga1.x + be1.x;
+        f[k].v[5] = (f[k].v[5] - m1) * r1 * ga1.y + be1.y;
+        f[k].v[6] = (f[k].v[6] - m1) * r1 * ga1.z + be1.z;
+        f[k].v[7] = (f[k].v[7] - m1) * r1 * ga1.w + be1.w;
+      }
+      if (act == CTTA_ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[k].v[i] = __fdividef(f[k].v[i], 1.f + __expf(-f[k].v[i]));
+      }
+      if (!up) {
+        store8(y, y_dtype, (img_row0 + pix[k]) * y_ld + ch[k], f[k]);
+      } else {
+        const int ph = pix[k] / w, pw = pix[k] - ph * w;
+        const int w2 = 2 * w;
+        const long long o = (static_cast<long long>(n) * 4 * hw + static_cast<long long>(2 * ph) * w2 + 2 * pw);
+        store8(y, y_dtype, o * y_ld + ch[k], f[k]);
+        store8(y, y_dtype, (o + 1) * y_ld + ch[k], f[k]);
+        store8(y, y_dtype, (o + w2) * y_ld + ch[k], f[k]);
+        store8(y, y_dtype, (o + w2 + 1) * y_ld + ch[k], f[k]);
+      }
     }
   }
 }
@@ -244,8 +315,10 @@ extern "C" int ctta_groupnorm_apply(const void* x, int32_t x_dtype, int32_t c, i
                                     int32_t raw_ld, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   CTTA_REQUIRE(x && y && n_img > 0 && h > 0 && w > 0, "groupnorm_apply: null / empty input");
-  CTTA_REQUIRE(c % 4 == 0 && c2 % 4 == 0 && ld % 4 == 0 && ld2 % 4 == 0 && y_ld % 4 == 0 && raw_ld % 4 == 0,
-               "groupnorm_apply: channels and strides must be multiples of 4");
+  CTTA_REQUIRE(c % 8 == 0 && c2 % 8 == 0 && ld % 8 == 0 && ld2 % 8 == 0 && y_ld % 8 == 0 && raw_ld % 8 == 0,
+               "groupnorm_apply: channels and strides must be multiples of 8");
+  CTTA_REQUIRE(static_cast<long long>(h) * w * ((c + c2) / 8) < (1LL << 31) - (1 << 24),
+               "groupnorm_apply: image too large for 32-bit indexing");
   CTTA_REQUIRE(al16(x) && (!x2 || al16(x2)) && al16(y) && (!raw_out || al16(raw_out)),
                "groupnorm_apply: tensors must be 16-byte aligned");
   if (stats) {
@@ -255,9 +328,9 @@ extern "C" int ctta_groupnorm_apply(const void* x, int32_t x_dtype, int32_t c, i
   }
   CTTA_REQUIRE(!(raw_out && upsample2x), "groupnorm_apply: raw_out and upsample are exclusive");
   CTTA_REQUIRE(act == CTTA_ACT_NONE || act == CTTA_ACT_SILU, "groupnorm_apply: act must be NONE or SILU");
-  const long long total = static_cast<long long>(h) * w * ((c + c2) / 4);
-  long long blocks = (total + 255) / 256;
-  const long long cap = (static_cast<long long>(sm_count()) * 16 + n_img - 1) / n_img;
+  const long long total = static_cast<long long>(h) * w * ((c + c2) / 8);
+  long long blocks = (total + 256 * kGnItems - 1) / (256 * kGnItems);
+  const long long cap = (static_cast<long long>(sm_count()) * 32 + n_img - 1) / n_img;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   dim3 grid(static_cast<unsigned>(blocks), n_img);

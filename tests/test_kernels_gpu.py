@@ -224,6 +224,38 @@ def test_attention(b, h, lq, lk, masked):
     assert rel(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("b,h,lq,lk,masked,amp", [(2, 5, 4096, 4096, False, 1.0), (2, 3, 300, 500, True, 1.0),
+                                                  (1, 2, 128, 128, False, 1.0), (2, 2, 640, 1152, True, 8.0),
+                                                  (1, 1, 256, 2048, False, 20.0)])
+def test_attention_tcgen05_strided(b, h, lq, lk, masked, amp):
+    """Self-attention sized problems run on the tcgen05 kernel: q/k/v are strided views of one fused buffer (the
+    UNet's qkv GEMM output); `amp` scales the scores so that the running max moves by more than the lazy-rescale
+    threshold between key tiles; ragged lq / lk exercise TMA zero fill and the key-length mask."""
+    torch.manual_seed(12)
+    d = 64
+    lm = max(lq, lk)
+    buf = torch.randn(b, lm, 3, h, d, device=DEV)
+    buf[:, :, 0] *= amp
+    # make the max grow along the key axis so the rescale path is taken repeatedly
+    buf[:, :, 1] *= torch.linspace(0.2, 1.0, lm, device=DEV)[None, :, None, None]
+    buf[..., 51:] = 0
+    buf16 = buf.to(DT)
+    q, k, v = buf16[:, :lq, 0], buf16[:, :lk, 1], buf16[:, :lk, 2]
+    scale = 51 ** -0.5
+    kv_len = None
+    bias = None
+    if masked:
+        kv_len = torch.randint(1, lk + 1, (b,), device=DEV, dtype=torch.int32)
+        kv_len[0] = lk
+        mask = torch.arange(lk, device=DEV)[None, :] < kv_len[:, None]
+        bias = torch.zeros(b, 1, 1, lk, device=DEV).masked_fill(~mask[:, None, None, :], float("-inf"))
+    ref = F.scaled_dot_product_attention(q.float().permute(0, 2, 1, 3), k.float().permute(0, 2, 1, 3),
+                                         v.float().permute(0, 2, 1, 3), attn_mask=bias, scale=scale).permute(0, 2, 1, 3)
+    out = ops.attention(q, k, v, scale, kv_len=kv_len)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < 3e-3
+
+
 def test_softmax_rows():
     torch.manual_seed(10)
     x = torch.randn(300, 4096, device=DEV) * 20
