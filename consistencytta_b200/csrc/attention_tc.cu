@@ -1,9 +1,10 @@
 // Fused flash-style self-attention on tcgen05 tensor cores for head_dim 64 (the UNet's 51-wide heads padded to 64).
 //
 // One CTA = one (batch, head) and 256 query rows = two independent 128-row tiles that share every K/V tile.
-// 10 warps: warp 0 = TMA loader (Q once, K/V through a 3-stage ring), warp 1 = single-thread tcgen05.mma issuer,
-// warps 2..5 / 6..9 = softmax warp groups of query tile 0 / 1 (thread == query row, so the row max / row sum need no
-// shuffles).  Per key tile of 128:
+// 12 warps: warps 0..3 / 4..7 = softmax warp groups of query tile 0 / 1 (thread == query row, so the row max / row sum
+// need no shuffles; setmaxnreg gives them 224 registers), warp 8 = TMA loader (Q once, K/V through a 3-stage ring),
+// warp 9 = single-thread tcgen05.mma issuer.  The two softmax groups share the SM's MUFU pipes, so group 1 starts half
+// an iteration late: one group's exponentials then overlap the other's TMEM loads / packing / stores.  Per key tile of 128:
 //     S_t   = Q_t K^T            UMMA 128x128x64, fp32 in TMEM (S_t: 128 columns)
 //     P_t   = exp2(c S_t - c m)  softmax warps: tcgen05.ld -> registers -> 16-bit P into swizzled shared memory
 //     O_t  += P_t V              UMMA 128x64x128, V is the MN-major B operand exactly as TMA lands it ([keys, d])
@@ -29,7 +30,8 @@ constexpr int kTile = 128;                   // query rows per tile == keys per 
 constexpr int kD = 64;
 constexpr int kTileBytes = kTile * kD * 2;   // 16 KiB: one [128 x 64] 16-bit operand tile (rows of 128 B, SW128)
 constexpr int kStages = 3;
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;
+constexpr int kLoaderWarp = 8, kMmaWarp = 9;
 constexpr int kSmemQ = 0;
 constexpr int kSmemKV = kSmemQ + 2 * kTileBytes;             // K then V per stage
 constexpr int kSmemP = kSmemKV + kStages * 2 * kTileBytes;   // per query tile: two [128 x 64] K-major halves
@@ -91,6 +93,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __shared__ __align__(8) uint64_t bar_q_full;
   __shared__ __align__(8) uint64_t bar_kv_full[kStages], bar_kv_empty[kStages];
   __shared__ __align__(8) uint64_t bar_s_full[2], bar_s_free[2], bar_p_full[2], bar_pv_done[2];
+  __shared__ __align__(8) uint64_t bar_stagger;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -114,12 +117,13 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_init(smem_u32(&bar_p_full[t]), 4);
       mbar_init(smem_u32(&bar_pv_done[t]), 1);
     }
+    mbar_init(smem_u32(&bar_stagger), 4);
     mbar_fence_init();
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
     tmem_relinquish();
   }
@@ -128,7 +132,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp == 0) {
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+  if (warp == kLoaderWarp) {
     // ------------------------------------------------------------------ TMA loader
     if (elect_one_sync()) {
       const uint32_t qf = smem_u32(&bar_q_full);
@@ -150,7 +156,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one_sync()) {
       const uint32_t idesc_qk = umma_idesc(kTile, kTile, p.is_bf16);                 // 128 x 128, A and B K-major
@@ -201,9 +207,11 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         umma_commit(smem_u32(&bar_kv_empty[stage]));
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------------------------------------------ softmax warps (thread == query row)
-    const int t = (warp - 2) >> 2;                  // query tile of this warp group
+    const int t = warp >> 2;                        // query tile of this warp group
     const int q = warp & 3;                         // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;                  // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -265,6 +273,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           tmem_st_wait();
         }
       }
+      if (j == 0 && t == 1) mbar_wait(smem_u32(&bar_stagger), 0);   // start half an iteration behind group 0
       const float mc = m_used * c;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
@@ -279,6 +288,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         l3 += s[i + 3];
       }
       l_sum += (l0 + l1) + (l2 + l3);
+      if (j == 0 && t == 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_stagger));
+      }
       if (j > 0 && !waited_pv) mbar_wait(smem_u32(&bar_pv_done[t]), par ^ 1u);   // PV(j-1) no longer reads P_t
 #pragma unroll
       for (int ck = 0; ck < 16; ++ck) {
@@ -319,7 +332,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }

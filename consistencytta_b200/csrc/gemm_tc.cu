@@ -85,7 +85,20 @@ struct GemmKParams {
   // which amortises the per-tile hand-offs when a 128 x N tile is only a few hundred cycles of work
   int sub_tiles;
   int epi_groups;          // 1 or 2 groups of 4 epilogue warps (2 = alternate chunks between the groups)
+  int acc_single;          // 1: one accumulator stage (sub_tiles * block_n * 2 > 512 TMEM columns), else two
+  // stream mode (multi-tap convolutions): per (channel chunk, tap group) ONE halo'd activation box is loaded into
+  // the A ring and every tap of the group is a row-shifted UMMA view of it; weight chunks stream through their own
+  // ring and are shared by the sub_tiles of an M super-tile.  Cuts the L2 -> shared-memory traffic per FLOP by the
+  // number of taps (A) and by sub_tiles (W), which is what bounds the tap-by-tap mainloop (~14 TB/s chip-wide).
+  int stream;
+  int n_groups;                       // tap groups: CONV1D 1, CONV2D one per distinct horizontal shift
+  short grp_first[4], grp_count[4], grp_shift[4];   // taps [first, first+count) of a group; box shift along w
+  short tap_id[CTTA_MAX_TAPS];        // original tap index (column block of the packed weights)
+  short tap_rows[CTTA_MAX_TAPS];      // row offset of the tap's view inside the box
+  int a_loads, a_box_rows, a_stage_bytes, n_a_stages, a_row0_shift;
+  int w_stage_bytes, w_ring_off;
 };
+constexpr int kMaxAStages = 3;
 
 struct TileCoord {
   int n0;          // first output channel of the tile
@@ -322,6 +335,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __shared__ __align__(8) uint64_t bar_ring_full[kMaxRing];
   __shared__ __align__(8) uint64_t bar_ring_empty[kMaxRing];
   __shared__ __align__(8) uint64_t bar_weights;
+  __shared__ __align__(8) uint64_t bar_a_full[kMaxAStages];
+  __shared__ __align__(8) uint64_t bar_a_empty[kMaxAStages];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -342,6 +357,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(smem_u32(&bar_ring_empty[s]), 4);
     }
     mbar_init(smem_u32(&bar_weights), 1);
+    for (int s = 0; s < kMaxAStages; ++s) {
+      mbar_init(smem_u32(&bar_a_full[s]), 1);
+      mbar_init(smem_u32(&bar_a_empty[s]), 1);
+    }
     mbar_fence_init();
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -367,7 +386,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane)
     const bool leader = elect_one_sync();
-    if (leader && p.halo) {
+    if (leader && p.stream) {
+      int a_stage = 0, w_stage = 0;
+      uint32_t a_phase = 0, w_phase = 0;
+      const uint32_t a_box_bytes = static_cast<uint32_t>(p.a_box_rows * 128);
+      const uint32_t w_base = tiles_base + static_cast<uint32_t>(p.w_ring_off);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int g = 0; g < p.n_groups; ++g) {
+            mbar_wait(smem_u32(&bar_a_empty[a_stage]), a_phase ^ 1u);
+            const uint32_t afull = smem_u32(&bar_a_full[a_stage]);
+            mbar_arrive_expect_tx(afull, a_box_bytes * p.a_loads);
+            const uint32_t a_dst = tiles_base + static_cast<uint32_t>(a_stage * p.a_stage_bytes);
+            if (p.a_mode == CTTA_A_CONV1D) {
+              for (int l = 0; l < p.a_loads; ++l)
+                tma_load_3d(a_dst + l * a_box_bytes, &tmap_a, afull, kc * kBlockK,
+                            tc.c1 + p.a_row0_shift + l * p.a_box_rows, tc.c2);
+            } else {
+              tma_load_4d(a_dst, &tmap_a, afull, kc * kBlockK, p.grp_shift[g], tc.c2 + p.a_row0_shift, tc.c3);
+            }
+            if (++a_stage == p.n_a_stages) {
+              a_stage = 0;
+              a_phase ^= 1u;
+            }
+            const int j1 = p.grp_first[g] + p.grp_count[g];
+            for (int j = p.grp_first[g]; j < j1; ++j) {
+              mbar_wait(smem_u32(&bar_empty[w_stage]), w_phase ^ 1u);
+              const uint32_t wfull = smem_u32(&bar_full[w_stage]);
+              mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(p.w_stage_bytes));
+              tma_load_2d(w_base + w_stage * p.w_stage_bytes, &tmap_b, wfull, (p.tap_id[j] * p.k_chunks + kc) * kBlockK,
+                          tc.n0);
+              if (++w_stage == p.n_stages) {
+                w_stage = 0;
+                w_phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    } else if (leader && p.halo) {
       // resident weights: one {64 x block_n} box per tap, loaded once per CTA
       const uint32_t wbar = smem_u32(&bar_weights);
       mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(p.w_bytes));
@@ -427,15 +485,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one lane)
     const bool leader = elect_one_sync();
-    if (leader && p.halo) {
+    if (leader && p.stream) {
+      const uint32_t idesc = umma_idesc(kBlockM, p.block_n, p.is_bf16);
+      int a_stage = 0, w_stage = 0;
+      uint32_t a_phase = 0, w_phase = 0;
+      const uint32_t w_base = tiles_base + static_cast<uint32_t>(p.w_ring_off);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = p.acc_single ? 0 : (it & 1);
+        const uint32_t acc_phase = p.acc_single ? (it & 1) : ((it >> 1) & 1);
+        mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
+        uint32_t started = 0;   // 0 until the first MMA of every sub-tile has been issued
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          const int nkk = (kc == p.k_chunks - 1) ? p.kk_last : kBlockK / 16;
+          for (int g = 0; g < p.n_groups; ++g) {
+            mbar_wait(smem_u32(&bar_a_full[a_stage]), a_phase);
+            const uint32_t a_base = tiles_base + static_cast<uint32_t>(a_stage * p.a_stage_bytes);
+            const int j1 = p.grp_first[g] + p.grp_count[g];
+            for (int j = p.grp_first[g]; j < j1; ++j) {
+              mbar_wait(smem_u32(&bar_full[w_stage]), w_phase);
+              tc_fence_after();
+              const uint32_t b_addr = w_base + static_cast<uint32_t>(w_stage * p.w_stage_bytes);
+              const uint32_t a_tap = a_base + static_cast<uint32_t>(p.tap_rows[j]) * 128u;
+              for (int sub = 0; sub < p.sub_tiles; ++sub) {
+                const uint32_t a_addr = a_tap + static_cast<uint32_t>(sub * kBlockM * 128);
+#pragma unroll
+                for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                  if (kk < nkk)
+                    umma_f16(d_tmem + sub * p.block_n, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32),
+                             idesc, (started | kk) != 0 ? 1u : 0u);
+                }
+              }
+              started = 1;
+              umma_commit(smem_u32(&bar_empty[w_stage]));
+              if (++w_stage == p.n_stages) {
+                w_stage = 0;
+                w_phase ^= 1u;
+              }
+            }
+            umma_commit(smem_u32(&bar_a_empty[a_stage]));
+            if (++a_stage == p.n_a_stages) {
+              a_stage = 0;
+              a_phase ^= 1u;
+            }
+          }
+        }
+        umma_commit(smem_u32(&bar_tmem_full[acc]));
+      }
+    } else if (leader && p.halo) {
       const uint32_t idesc = umma_idesc(kBlockM, p.block_n, p.is_bf16);
       mbar_wait(smem_u32(&bar_weights), 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = p.acc_single ? 0 : (it & 1);
+        const uint32_t acc_phase = p.acc_single ? (it & 1) : ((it >> 1) & 1);
         mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
         for (int sub = 0; sub < p.sub_tiles; ++sub) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
@@ -466,8 +573,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = p.acc_single ? 0 : (it & 1);
+        const uint32_t acc_phase = p.acc_single ? (it & 1) : ((it >> 1) & 1);
         mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
         tc_fence_after();
         for (int sub = 0; sub < p.sub_tiles; ++sub) {
@@ -553,8 +660,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int lr = q * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = p.acc_single ? 0 : (it & 1);
+      const uint32_t acc_phase = p.acc_single ? (it & 1) : ((it >> 1) & 1);
       const TileCoord tc = decode_tile(p, tile);
       // logical row -> (image, row in image) -> output row
       int img, r;
@@ -650,8 +757,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t my_ctr = 0;    // chunks processed by this warp (staging buffer parity)
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = p.acc_single ? 0 : (it & 1);
+      const uint32_t acc_phase = p.acc_single ? (it & 1) : ((it >> 1) & 1);
       const TileCoord tc = decode_tile(p, tile);
       int row0, img0;
       if (p.a_mode == CTTA_A_ROWS) {
@@ -664,14 +771,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // this warp's 32 rows: coordinates of the store box (of sub-tile 0)
       const int st_row0 = row0 + wrow_in_img - p.row_coord_shift;
       const int st_img = img0 + wimg;
-      long long ra_row = 0;
-      if (has_rowadd) {  // (host guarantees sub_tiles == 1 with rowadd)
+      long long ra_gr0 = 0, ra_gmax = 0;   // global logical row of this thread (sub-tile 0) for the per-image row add
+      if (has_rowadd) {
         const int r_in_img = (p.a_mode == CTTA_A_CONV2D) ? (row0 + (lr % p.out_rows_tile_img)) : (row0 + lr);
         const int img = (p.a_mode == CTTA_A_CONV2D) ? (img0 + lr / p.out_rows_tile_img) : img0;
-        long long gr = static_cast<long long>(img) * p.rows_per_img + r_in_img;
-        const long long gmax = static_cast<long long>(p.n_img) * p.rows_per_img - 1;
-        if (gr > gmax) gr = gmax;  // rows past the end are clipped by the TMA store; keep the load in bounds
-        ra_row = gr / p.rowadd_rows;
+        ra_gr0 = static_cast<long long>(img) * p.rows_per_img + r_in_img;
+        ra_gmax = static_cast<long long>(p.n_img) * p.rows_per_img - 1;  // rows past the end are clipped by the TMA store
       }
       // bias of this tile -> shared memory (double buffered by tile parity)
       float* bs = bias_s + (it & 1) * 256;
@@ -702,7 +807,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // per-row additive term (time embedding): issue the loads before waiting on TMEM / the ring
         float4 ra[8];
         if (has_rowadd) {
-          const float* rp = p.rowadd + ra_row * p.rowadd_ld + col;
+          long long gr = ra_gr0 + sub * kBlockM;
+          if (gr > ra_gmax) gr = ra_gmax;   // keep the load in bounds
+          const float* rp = p.rowadd + (gr / p.rowadd_rows) * p.rowadd_ld + col;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             if (col + 4 * g + 3 < p.N) ra[g] = __ldg(reinterpret_cast<const float4*>(rp + 4 * g));
@@ -1102,8 +1209,128 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   if (d->act == CTTA_ACT_GEGLU && d->out_dtype == CTTA_F32) tma_ok = false;
   if (d->bias && !((reinterpret_cast<uintptr_t>(d->bias) & 3) == 0)) tma_ok = false;
   if (d->rowadd && (!aligned16(d->rowadd) || d->rowadd_ld % 4)) tma_ok = false;
+  // ---- stream mode (see GemmKParams::stream): multi-tap convolutions whose epilogue can go through TMA
+  p.sub_tiles = 1;
+  if (tma_ok && !p.halo && d->ntaps > 1 && d->a_mode != CTTA_A_ROWS && getenv("CTTA_NO_STREAM") == nullptr) {
+    int st = 512 / block_n;            // sub-tiles sharing one weight chunk; all accumulators must fit 512 TMEM columns
+    if (st > 4) st = 4;
+    if (block_n > 128 && st > 2) st = 2;
+    bool ok = false;
+    int box_rows = 0, a_loads = 1, a_stage = 0, box_h = 0;
+    if (d->a_mode == CTTA_A_CONV1D) {
+      int min_shift = p.tap_d0[0], max_shift = p.tap_d0[0];
+      for (int j = 1; j < d->ntaps; ++j) {
+        if (p.tap_d0[j] < min_shift) min_shift = p.tap_d0[j];
+        if (p.tap_d0[j] > max_shift) max_shift = p.tap_d0[j];
+      }
+      const long long row_tiles = (p.rows_per_img + kBlockM - 1) / kBlockM;
+      while (st > 1 && ((row_tiles + st - 1) / st) * d->n_img * p.n_tiles_n < 2LL * sm_count()) st /= 2;
+      const int need = st * kBlockM + (max_shift - min_shift);
+      a_loads = (need + 255) / 256;
+      box_rows = ((need + a_loads - 1) / a_loads + 7) / 8 * 8;
+      a_stage = (a_loads * box_rows * 128 + 1023) / 1024 * 1024;
+      p.n_groups = 1;
+      p.grp_first[0] = 0;
+      p.grp_count[0] = static_cast<short>(d->ntaps);
+      p.grp_shift[0] = 0;
+      for (int j = 0; j < d->ntaps; ++j) {
+        p.tap_id[j] = static_cast<short>(j);
+        p.tap_rows[j] = static_cast<short>(p.tap_d0[j] - min_shift);
+      }
+      p.a_row0_shift = min_shift;
+      ok = true;
+    } else {
+      // CONV2D: a tile is box_h full-width image rows = st * 128 pixels of ONE image; one box per horizontal shift
+      // holds rows [h0 + dh_min, h0 + box_h + dh_max) so the taps sharing that shift are row-shifted views of it
+      int dh_min = 0, dh_max = 0, dws[4], ndw = 0;
+      bool taps_ok = true;
+      for (int j = 0; j < d->ntaps; ++j) {
+        if (p.tap_d1[j] < dh_min) dh_min = p.tap_d1[j];
+        if (p.tap_d1[j] > dh_max) dh_max = p.tap_d1[j];
+        int k = 0;
+        while (k < ndw && dws[k] != p.tap_d0[j]) ++k;
+        if (k == ndw) {
+          if (ndw == 4) { taps_ok = false; break; }
+          dws[ndw++] = p.tap_d0[j];
+        }
+      }
+      for (; st >= 1 && taps_ok; st /= 2) {
+        const int pix = st * kBlockM;
+        if (d->w <= kBlockM && pix % d->w == 0 && d->h % (pix / d->w) == 0 &&
+            static_cast<long long>(d->h / (pix / d->w)) * d->n_img * p.n_tiles_n >= (st > 1 ? 2LL * sm_count() : 1)) {
+          box_h = pix / d->w;
+          ok = box_h + (dh_max - dh_min) <= 256;
+          break;
+        }
+      }
+      if (ok) {
+        box_rows = (box_h + dh_max - dh_min) * d->w;
+        a_stage = (box_rows * 128 + 1023) / 1024 * 1024;
+        p.n_groups = ndw;
+        int t = 0;
+        for (int g = 0; g < ndw; ++g) {
+          p.grp_first[g] = static_cast<short>(t);
+          p.grp_shift[g] = static_cast<short>(dws[g]);
+          for (int j = 0; j < d->ntaps; ++j) {
+            if (p.tap_d0[j] != dws[g]) continue;
+            p.tap_id[t] = static_cast<short>(j);
+            p.tap_rows[t] = static_cast<short>((p.tap_d1[j] - dh_min) * d->w);
+            ++t;
+          }
+          p.grp_count[g] = static_cast<short>(t - p.grp_first[g]);
+        }
+        p.a_row0_shift = dh_min;
+      }
+    }
+    // shared-memory feasibility: 2 A stages + 2 weight stages + the smallest epilogue plan
+    const int w_stage = block_n * 128;
+    const bool f32o = d->out && d->out_dtype == CTTA_F32;
+    const int min_epi = ((f32o || d->residual) ? 2 * kRingSlotBytes : 0) +
+                        (((d->out && !f32o) || d->out2) ? 4 * 2 * kStage16Bytes : 0) + kBiasBytes;
+    if (ok && 2 * a_stage + 2 * w_stage + min_epi <= kSmemBudget) {
+      p.stream = 1;
+      p.sub_tiles = st;
+      p.a_loads = a_loads;
+      p.a_box_rows = box_rows;
+      p.a_stage_bytes = a_stage;
+      p.n_a_stages = 2;
+      if (3 * a_stage + 4 * w_stage + min_epi + 2 * kRingSlotBytes + 4 * 2 * kStage16Bytes <= kSmemBudget) p.n_a_stages = 3;
+      p.w_stage_bytes = w_stage;
+      p.stage_bytes = w_stage;                       // the generic planner below sizes the weight ring
+      p.tiles_off = p.n_a_stages * a_stage;          // ... after the A ring
+      p.w_ring_off = p.tiles_off;
+      int acc = 32;
+      while (acc < st * block_n) acc *= 2;
+      p.acc_stride = acc;
+      p.acc_single = 2 * acc > 512 ? 1 : 0;
+      p.tmem_cols = p.acc_single ? acc : 2 * acc;
+      if (d->a_mode == CTTA_A_CONV1D) {
+        const long long row_tiles = (p.rows_per_img + kBlockM - 1) / kBlockM;
+        p.tiles_per_img = static_cast<int>((row_tiles + st - 1) / st);
+        p.n_tiles_m = p.tiles_per_img * d->n_img;
+        cuuint64_t dims[3] = {(cuuint64_t)d->c, (cuuint64_t)d->w, (cuuint64_t)d->n_img};
+        cuuint64_t strides[2] = {(cuuint64_t)d->a_ld * esz, (cuuint64_t)d->a_ld * esz * (cuuint64_t)d->w};
+        cuuint32_t box[3] = {kBlockK, (cuuint32_t)box_rows, 1};
+        int rc = make_tmap(&tmap_a, p.is_bf16, d->a, 3, dims, strides, box);
+        if (rc) return rc;
+      } else {
+        p.box_w = d->w;
+        p.box_h = box_h;
+        p.box_n = 1;
+        p.tiles_w = 1;
+        p.tiles_h = d->h / box_h;
+        p.n_tiles_m = p.tiles_h * d->n_img;
+        cuuint64_t dims[4] = {(cuuint64_t)d->c, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n_img};
+        cuuint64_t s1 = (cuuint64_t)d->a_ld * esz;
+        cuuint64_t strides[3] = {s1, s1 * (cuuint64_t)d->w, s1 * (cuuint64_t)d->w * (cuuint64_t)d->h};
+        cuuint32_t box[4] = {kBlockK, (cuuint32_t)d->w, (cuuint32_t)(box_rows / d->w), 1};
+        int rc = make_tmap(&tmap_a, p.is_bf16, d->a, 4, dims, strides, box);
+        if (rc) return rc;
+      }
+    }
+  }
   int rows_tile_img = kBlockM;
-  if (d->a_mode == CTTA_A_CONV2D) {
+  if (d->a_mode == CTTA_A_CONV2D && !p.stream) {
     rows_tile_img = kBlockM / p.box_n;
     if (p.tiles_w != 1 || rows_tile_img % 32 != 0) tma_ok = false;
   }
@@ -1111,8 +1338,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   p.epi_tma = tma_ok ? 1 : 0;
   p.epi_groups = 1;
   // M super-tiles for narrow N (see GemmKParams::sub_tiles)
-  p.sub_tiles = 1;
-  if (tma_ok && d->a_mode != CTTA_A_CONV2D && !d->rowadd && block_n <= 128 && getenv("CTTA_NO_SUPERTILE") == nullptr) {
+  if (!p.stream && tma_ok && d->a_mode != CTTA_A_CONV2D && !d->rowadd && block_n <= 128 && getenv("CTTA_NO_SUPERTILE") == nullptr) {
     int st = 256 / block_n;
     if (st > 4) st = 4;
     const long long row_tiles = (p.rows_per_img + kBlockM - 1) / kBlockM;
