@@ -29,7 +29,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                         // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 352;                        // 3 control warps + 8 epilogue warps
+constexpr int kThreads = 384;                        // 3 control warps + 8 epilogue warps + the stream-mode A loader
+constexpr int kALoaderWarp = 11;
 constexpr int kSmemMaxDynamic = 232448 - 1024;     // 227 KiB minus the static barriers
 constexpr int kSmemBudget = kSmemMaxDynamic - 1024;  // minus alignment slack
 constexpr int kEpiWarp0 = 3;                         // first of the 4 epilogue math warps
@@ -85,6 +86,9 @@ struct GemmKParams {
   // which amortises the per-tile hand-offs when a 128 x N tile is only a few hundred cycles of work
   int sub_tiles;
   int epi_groups;          // 1 or 2 groups of 4 epilogue warps (2 = alternate chunks between the groups)
+  // fused GroupNorm moments of the OUTPUT (sum, sum of squares per (image, group)), accumulated with atomics
+  float* stats;
+  int stats_groups, stats_cpg, stats_rows;   // channels per group (power of two >= 4); logical rows per image
   int acc_single;          // 1: one accumulator stage (sub_tiles * block_n * 2 > 512 TMEM columns), else two
   // stream mode (multi-tap convolutions): per (channel chunk, tap group) ONE halo'd activation box is loaded into
   // the A ring and every tap of the group is a row-shifted UMMA view of it; weight chunks stream through their own
@@ -322,6 +326,49 @@ __device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
   return r;
 }
 
+// GroupNorm moments of one 32-column chunk: v[32] = this thread's row, NG = groups inside the chunk (32 / cpg, or 1
+// when a group spans the whole chunk).  Rows are summed across the warp with a halving butterfly (NG * 2 values ->
+// one value per lane after log2(2 NG) exchange steps), then one red.global per (group, moment).
+template <int NG>
+__device__ __forceinline__ void stats_chunk(const float* v, bool row_valid, int lane, float* dst /* [groups][2] */,
+                                            int g0, int groups) {
+  constexpr int CPG = 32 / NG;
+  constexpr int NV = 2 * NG;
+  float a[NV];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPG; ++i) {
+      const float x = row_valid ? v[g * CPG + i] : 0.f;
+      s += x;
+      q = fmaf(x, x, q);
+    }
+    a[2 * g] = s;
+    a[2 * g + 1] = q;
+  }
+  int idx = 0;       // index of the value this lane ends up owning
+  int mask = 16;
+#pragma unroll
+  for (int step = NV / 2; step >= 1; step /= 2, mask /= 2) {
+    const bool upper = (lane & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      const float send = upper ? a[i] : a[i + step];
+      const float keep = upper ? a[i + step] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+    if (upper) idx += step;
+  }
+  // a[0] now holds value `idx` summed over the lanes that differ in the bits already consumed
+  float r = a[0];
+  for (; mask >= 1; mask /= 2) r += __shfl_xor_sync(0xffffffffu, r, mask);
+  constexpr int kUsedBits = (NV == 2) ? 1 : (NV == 4) ? 2 : (NV == 8) ? 3 : 4;
+  const int low = lane & ((16 >> (kUsedBits - 1)) - 1);   // lanes sharing one value: only low == 0 writes
+  const int g = g0 + (idx >> 1);
+  if (low == 0 && g < groups) atomicAdd(dst + 2 * g + (idx & 1), r);
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -387,40 +434,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ------------------------------------------------------------------ TMA producer (one lane)
     const bool leader = elect_one_sync();
     if (leader && p.stream) {
-      int a_stage = 0, w_stage = 0;
-      uint32_t a_phase = 0, w_phase = 0;
-      const uint32_t a_box_bytes = static_cast<uint32_t>(p.a_box_rows * 128);
+      // weight chunks only; the halo'd activation boxes come from their own loader warp (kALoaderWarp) so that a box is
+      // requested as soon as its ring slot frees up, independent of the weight ring's back-pressure
+      int w_stage = 0;
+      uint32_t w_phase = 0;
       const uint32_t w_base = tiles_base + static_cast<uint32_t>(p.w_ring_off);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          for (int g = 0; g < p.n_groups; ++g) {
-            mbar_wait(smem_u32(&bar_a_empty[a_stage]), a_phase ^ 1u);
-            const uint32_t afull = smem_u32(&bar_a_full[a_stage]);
-            mbar_arrive_expect_tx(afull, a_box_bytes * p.a_loads);
-            const uint32_t a_dst = tiles_base + static_cast<uint32_t>(a_stage * p.a_stage_bytes);
-            if (p.a_mode == CTTA_A_CONV1D) {
-              for (int l = 0; l < p.a_loads; ++l)
-                tma_load_3d(a_dst + l * a_box_bytes, &tmap_a, afull, kc * kBlockK,
-                            tc.c1 + p.a_row0_shift + l * p.a_box_rows, tc.c2);
-            } else {
-              tma_load_4d(a_dst, &tmap_a, afull, kc * kBlockK, p.grp_shift[g], tc.c2 + p.a_row0_shift, tc.c3);
-            }
-            if (++a_stage == p.n_a_stages) {
-              a_stage = 0;
-              a_phase ^= 1u;
-            }
-            const int j1 = p.grp_first[g] + p.grp_count[g];
-            for (int j = p.grp_first[g]; j < j1; ++j) {
-              mbar_wait(smem_u32(&bar_empty[w_stage]), w_phase ^ 1u);
-              const uint32_t wfull = smem_u32(&bar_full[w_stage]);
-              mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(p.w_stage_bytes));
-              tma_load_2d(w_base + w_stage * p.w_stage_bytes, &tmap_b, wfull, (p.tap_id[j] * p.k_chunks + kc) * kBlockK,
-                          tc.n0);
-              if (++w_stage == p.n_stages) {
-                w_stage = 0;
-                w_phase ^= 1u;
-              }
+          for (int j = 0; j < p.ntaps; ++j) {   // taps are stored group by group
+            mbar_wait(smem_u32(&bar_empty[w_stage]), w_phase ^ 1u);
+            const uint32_t wfull = smem_u32(&bar_full[w_stage]);
+            mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(p.w_stage_bytes));
+            tma_load_2d(w_base + w_stage * p.w_stage_bytes, &tmap_b, wfull, (p.tap_id[j] * p.k_chunks + kc) * kBlockK,
+                        tc.n0);
+            if (++w_stage == p.n_stages) {
+              w_stage = 0;
+              w_phase ^= 1u;
             }
           }
         }
@@ -601,6 +631,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         }
         umma_commit(smem_u32(&bar_tmem_full[acc]));  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp == kALoaderWarp) {
+    // ------------------------------------------------------------------ stream mode: activation box loader (one lane)
+    if (elect_one_sync() && p.stream) {
+      int a_stage = 0;
+      uint32_t a_phase = 0;
+      const uint32_t a_box_bytes = static_cast<uint32_t>(p.a_box_rows * 128);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int g = 0; g < p.n_groups; ++g) {
+            mbar_wait(smem_u32(&bar_a_empty[a_stage]), a_phase ^ 1u);
+            const uint32_t afull = smem_u32(&bar_a_full[a_stage]);
+            mbar_arrive_expect_tx(afull, a_box_bytes * p.a_loads);
+            const uint32_t a_dst = tiles_base + static_cast<uint32_t>(a_stage * p.a_stage_bytes);
+            if (p.a_mode == CTTA_A_CONV1D) {
+              for (int l = 0; l < p.a_loads; ++l)
+                tma_load_3d(a_dst + l * a_box_bytes, &tmap_a, afull, kc * kBlockK,
+                            tc.c1 + p.a_row0_shift + l * p.a_box_rows, tc.c2);
+            } else {
+              tma_load_4d(a_dst, &tmap_a, afull, kc * kBlockK, p.grp_shift[g], tc.c2 + p.a_row0_shift, tc.c3);
+            }
+            if (++a_stage == p.n_a_stages) {
+              a_stage = 0;
+              a_phase ^= 1u;
+            }
+          }
+        }
       }
     }
   } else if (warp == 2) {
@@ -898,6 +957,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (p.out_scale != 1.f) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= p.out_scale;
+          }
+          if (p.stats != nullptr) {
+            // image of this warp's 32 rows (warp-uniform: the host checks stats_rows % 32 == 0) and row validity
+            int s_img;
+            bool rv;
+            if (p.a_mode == CTTA_A_CONV2D) {
+              s_img = img0 + wimg;
+              rv = s_img < p.n_img;
+            } else {
+              const int r = row0 + sub * kBlockM + lr;
+              rv = r < p.rows_per_img;
+              s_img = (p.a_mode == CTTA_A_ROWS) ? (row0 + sub * kBlockM + wrow) / p.stats_rows : img0;
+              if (p.a_mode == CTTA_A_ROWS && !(row0 + sub * kBlockM + wrow < p.rows_per_img)) s_img = 0;  // all lanes invalid
+            }
+            float* sdst = p.stats + static_cast<long long>(s_img) * p.stats_groups * 2;
+            const int g0 = col / p.stats_cpg;
+            switch (p.stats_cpg) {
+              case 4: stats_chunk<8>(v, rv, lane, sdst, g0, p.stats_groups); break;
+              case 8: stats_chunk<4>(v, rv, lane, sdst, g0, p.stats_groups); break;
+              case 16: stats_chunk<2>(v, rv, lane, sdst, g0, p.stats_groups); break;
+              default: stats_chunk<1>(v, rv, lane, sdst, g0, p.stats_groups); break;   // cpg >= 32
+            }
           }
           if (out_f32) {
 #pragma unroll
@@ -1337,6 +1418,25 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   p.out_rows_tile_img = rows_tile_img;
   p.epi_tma = tma_ok ? 1 : 0;
   p.epi_groups = 1;
+  if (d->stats) {
+    const int cpg = d->stats_groups > 0 ? d->n / d->stats_groups : 0;
+    const bool pow2 = cpg >= 4 && (cpg & (cpg - 1)) == 0;
+    int n_stat_img = d->n_img;
+    bool ok = tma_ok && d->act != CTTA_ACT_GEGLU && d->out_stride == 1 && d->out_off == 0 && !d->accumulate && pow2 &&
+              d->stats_groups * cpg == d->n;
+    if (d->a_mode == CTTA_A_ROWS) {
+      ok = ok && d->stats_rows_per_img > 0 && d->stats_rows_per_img % 32 == 0 && d->rows_per_img % d->stats_rows_per_img == 0;
+      if (ok) n_stat_img = d->rows_per_img / d->stats_rows_per_img;
+    }
+    if (!ok)
+      return set_error(CTTA_ERR_UNSUPPORTED, "ctta_gemm: fused GroupNorm moments unsupported for this problem (n=%d groups=%d)",
+                       d->n, d->stats_groups);
+    CTTA_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * n_stat_img * d->stats_groups, stream));
+    p.stats = d->stats;
+    p.stats_groups = d->stats_groups;
+    p.stats_cpg = cpg;
+    p.stats_rows = d->a_mode == CTTA_A_ROWS ? d->stats_rows_per_img : 1;
+  }
   // M super-tiles for narrow N (see GemmKParams::sub_tiles)
   if (!p.stream && tma_ok && d->a_mode != CTTA_A_CONV2D && !d->rowadd && block_n <= 128 && getenv("CTTA_NO_SUPERTILE") == nullptr) {
     int st = 256 / block_n;
@@ -1455,6 +1555,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
       {N_, 1, 0, 1, 0, 0, N_, gemm_tc_kernel<EpiCfg<N_, 1, 0, 1, 0, 0, N_>>},  // fp32 out + time embedding
       {N_, 0, 0, 1, 0, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 0, 1, 0, 0, N_>>},  // fp32 out
       {N_, 0, 0, 0, 1, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 0, 0, 1, 0, N_>>},  // 16-bit out
+      {N_, 1, 0, 0, 1, 0, N_, gemm_tc_kernel<EpiCfg<N_, 1, 0, 0, 1, 0, N_>>},  // 16-bit out + time embedding
       {N_, 0, 1, 0, 1, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 1, 0, 1, 0, N_>>},  // 16-bit out + fp32 residual
       {G_, 0, 0, 0, 1, 0, N_, gemm_tc_kernel<EpiCfg<G_, 0, 0, 0, 1, 0, N_>>},  // GEGLU
   };

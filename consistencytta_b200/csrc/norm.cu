@@ -221,61 +221,91 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
-// One warp per row, row held in registers (ld <= 1024 fp32 -> <= 8 float4 per lane), two-pass variance.
+// One warp per group of R rows, rows held in registers (NV float4 per lane per row, R * NV = 8 so that every lane has
+// 128 B of loads in flight whatever the row length); two-pass variance; 16-bit output with zeroed pad columns.
+template <int NV, int R>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int m, int d, int ld,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         void* __restrict__ y, int y_dtype, int y_ld) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= m) return;
+  const int row0 = warp * R;
+  if (row0 >= m) return;
   const int nvec = ld >> 2;
-  const float* row = x + static_cast<long long>(warp) * ld;
-  float4 f[8];
-  float s = 0.f;
+  float4 f[R][NV];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int r = 0; r < R; ++r) {
+    const int row = min(row0 + r, m - 1);
+    const float4* src = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ld);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      f[r][i] = v < nvec ? __ldg(src + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float4 ga[NV], be[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
-    if (v < nvec) {
-      f[i] = *reinterpret_cast<const float4*>(row + 4 * v);
-      const int c0 = 4 * v;
-      if (c0 + 0 >= d) f[i].x = 0.f;
-      if (c0 + 1 >= d) f[i].y = 0.f;
-      if (c0 + 2 >= d) f[i].z = 0.f;
-      if (c0 + 3 >= d) f[i].w = 0.f;
-      s += (f[i].x + f[i].y) + (f[i].z + f[i].w);
+    ga[i] = v < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    be[i] = v < nvec ? __ldg(reinterpret_cast<const float4*>(beta) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float s[R], q[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    s[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = 4 * (lane + i * 32);
+      if (c0 + 0 >= d) f[r][i].x = 0.f;
+      if (c0 + 1 >= d) f[r][i].y = 0.f;
+      if (c0 + 2 >= d) f[r][i].z = 0.f;
+      if (c0 + 3 >= d) f[r][i].w = 0.f;
+      s[r] += (f[r][i].x + f[r][i].y) + (f[r][i].z + f[r][i].w);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / d;
-  float q = 0.f;
+  for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      const int c0 = 4 * v;
-      const float a = c0 + 0 < d ? f[i].x - mean : 0.f;
-      const float b = c0 + 1 < d ? f[i].y - mean : 0.f;
-      const float c = c0 + 2 < d ? f[i].z - mean : 0.f;
-      const float e = c0 + 3 < d ? f[i].w - mean : 0.f;
-      q += (a * a + b * b) + (c * c + e * e);
+    for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  }
+  const float inv_d = 1.f / d;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    s[r] *= inv_d;   // mean
+    q[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = 4 * (lane + i * 32);
+      const float a = c0 + 0 < d ? f[r][i].x - s[r] : 0.f;
+      const float b = c0 + 1 < d ? f[r][i].y - s[r] : 0.f;
+      const float c = c0 + 2 < d ? f[r][i].z - s[r] : 0.f;
+      const float e = c0 + 3 < d ? f[r][i].w - s[r] : 0.f;
+      q[r] += (a * a + b * b) + (c * c + e * e);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / d + eps);
+  for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      const int c0 = 4 * v;
-      float4 o4;
-      o4.x = c0 + 0 < d ? (f[i].x - mean) * rstd * gamma[c0 + 0] + beta[c0 + 0] : 0.f;
-      o4.y = c0 + 1 < d ? (f[i].y - mean) * rstd * gamma[c0 + 1] + beta[c0 + 1] : 0.f;
-      o4.z = c0 + 2 < d ? (f[i].z - mean) * rstd * gamma[c0 + 2] + beta[c0 + 2] : 0.f;
-      o4.w = c0 + 3 < d ? (f[i].w - mean) * rstd * gamma[c0 + 3] + beta[c0 + 3] : 0.f;
-      store4(y, y_dtype, static_cast<long long>(warp) * y_ld + c0, o4);
+    for (int r = 0; r < R; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= m) break;
+    const float rstd = rsqrtf(q[r] * inv_d + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        const int c0 = 4 * v;
+        float4 o4;
+        o4.x = c0 + 0 < d ? (f[r][i].x - s[r]) * rstd * ga[i].x + be[i].x : 0.f;
+        o4.y = c0 + 1 < d ? (f[r][i].y - s[r]) * rstd * ga[i].y + be[i].y : 0.f;
+        o4.z = c0 + 2 < d ? (f[r][i].z - s[r]) * rstd * ga[i].z + be[i].z : 0.f;
+        o4.w = c0 + 3 < d ? (f[r][i].w - s[r]) * rstd * ga[i].w + be[i].w : 0.f;
+        store4(y, y_dtype, static_cast<long long>(row0 + r) * y_ld + c0, o4);
+      }
     }
   }
 }
@@ -347,9 +377,19 @@ extern "C" int ctta_layernorm(const float* x, int32_t m, int32_t d, int32_t ld, 
   CTTA_REQUIRE(d > 0 && d <= ld && ld % 4 == 0 && ld <= 1024 && y_ld % 4 == 0 && y_ld >= ld,
                "layernorm: need d <= ld <= 1024, ld %% 4 == 0 (d=%d ld=%d)", d, ld);
   CTTA_REQUIRE(al16(x) && al16(y), "layernorm: tensors must be 16-byte aligned");
+  CTTA_REQUIRE(al16(gamma) && al16(beta), "layernorm: gamma / beta must be 16-byte aligned");
   const int warps_per_block = 8;
-  const int blocks = (m + warps_per_block - 1) / warps_per_block;
-  layernorm_kernel<<<blocks, 256, 0, stream>>>(x, m, d, ld, gamma, beta, eps, y, y_dtype, y_ld);
+  const int nv = (ld / 4 + 31) / 32;   // float4 per lane per row
+  if (nv <= 2) {
+    const int blocks = ((m + 3) / 4 + warps_per_block - 1) / warps_per_block;
+    layernorm_kernel<2, 4><<<blocks, 256, 0, stream>>>(x, m, d, ld, gamma, beta, eps, y, y_dtype, y_ld);
+  } else if (nv <= 4) {
+    const int blocks = ((m + 1) / 2 + warps_per_block - 1) / warps_per_block;
+    layernorm_kernel<4, 2><<<blocks, 256, 0, stream>>>(x, m, d, ld, gamma, beta, eps, y, y_dtype, y_ld);
+  } else {
+    const int blocks = (m + warps_per_block - 1) / warps_per_block;
+    layernorm_kernel<8, 1><<<blocks, 256, 0, stream>>>(x, m, d, ld, gamma, beta, eps, y, y_dtype, y_ld);
+  }
   CTTA_LAUNCH_CHECK();
   return 0;
 }

@@ -138,8 +138,10 @@ def pack_conv_transpose1d(weight, bias, stride, padding, dtype=None):
 # ------------------------------------------------------------------------------------------------ GEMM
 def gemm(a, pw, mode=A_ROWS, n_img=1, h=1, w=None, rows_per_img=None, a_ld=None, out=None, out_ld=None,
          out_rows_per_img=None, residual=None, res_ld=None, rowadd=None, rowadd_rows=1, act=ACT_NONE, act_slope=0.0,
-         accumulate=False, out_scale=1.0, out2=None, out2_ld=None, act2=ACT_NONE, act2_slope=0.0, use_bias=True):
-    """Launches ctta_gemm.  `a` is a 16-bit channels-last tensor; shapes are given explicitly by the caller."""
+         accumulate=False, out_scale=1.0, out2=None, out2_ld=None, act2=ACT_NONE, act2_slope=0.0, use_bias=True,
+         stats=None, stats_groups=32, stats_rows_per_img=0):
+    """Launches ctta_gemm.  `a` is a 16-bit channels-last tensor; shapes are given explicitly by the caller.
+    `stats` (fp32 [n_img, stats_groups, 2]) receives the GroupNorm moments of the result (fused statistics pass)."""
     _require_cuda(a)
     d = GemmDesc()
     d.a = a.data_ptr()
@@ -185,6 +187,10 @@ def gemm(a, pw, mode=A_ROWS, n_img=1, h=1, w=None, rows_per_img=None, a_ld=None,
     d.out_rows_per_img = out_rows_per_img if out_rows_per_img is not None else rows_per_img
     d.out_stride = pw.out_stride
     d.out_off = pw.out_off
+    if stats is not None:
+        d.stats = stats.data_ptr()
+        d.stats_groups = stats_groups
+        d.stats_rows_per_img = stats_rows_per_img
     check(lib().ctta_gemm(C.byref(d), _stream()))
     return out if out is not None else out2
 

@@ -216,32 +216,38 @@ class UNet2DConditionGuidedModel(PackedModule):
         return pk
 
     # ------------------------------------------------------------------ building blocks (channels-last)
-    def _resnet(self, pk, p, x, skip, temb_all, eps):
-        """ResnetBlock2D.forward, resnet.py:549-597. x fp32 [B,H,W,C1], skip fp32 [B,H,W,C2] or None (torch.cat)."""
+    def _resnet(self, pk, p, x, skip, temb_all, eps, x_stats=None, emit_stats=False):
+        """ResnetBlock2D.forward, resnet.py:549-597. x fp32 [B,H,W,C1], skip fp32 [B,H,W,C2] or None (torch.cat).
+        x_stats: GroupNorm moments of x already produced by the kernel that wrote x (fused statistics pass).
+        Returns (out, moments of out or None)."""
         b, h, w, _ = x.shape
         g = self.config["norm_num_groups"]
         has_sc = (p + ".conv_shortcut") in pk
         c_in = x.shape[-1] + (skip.shape[-1] if skip is not None else 0)
-        st = ops.groupnorm_stats(x, g, x2=skip)
+        st = x_stats if (x_stats is not None and skip is None) else ops.groupnorm_stats(x, g, x2=skip)
         raw = torch.empty(b, h, w, c_in, device=x.device, dtype=ops.OPERAND_DTYPE) if has_sc else None
         a = ops.groupnorm_apply(x, g, st, *pk[p + ".norm1"], eps=eps, act=ACT_SILU, x2=skip, raw_out=raw)
         c_out = pk[p + ".conv1"].n
         off = pk["temb_off"][p]
-        hid = torch.empty(b, h, w, c_out, device=x.device, dtype=torch.float32)
-        ops.conv2d(a, pk[p + ".conv1"], out=hid, rowadd=temb_all[:, off:off + c_out], rowadd_rows=h * w)
-        st2 = ops.groupnorm_stats(hid, g)
+        # conv1 + time embedding -> 16-bit hidden tensor (only GroupNorm 2 reads it) + its moments from the epilogue
+        hid = torch.empty(b, h, w, c_out, device=x.device, dtype=ops.OPERAND_DTYPE)
+        st2 = torch.empty(b, g, 2, device=x.device, dtype=torch.float32)
+        ops.conv2d(a, pk[p + ".conv1"], out=hid, rowadd=temb_all[:, off:off + c_out], rowadd_rows=h * w, stats=st2,
+                   stats_groups=g)
         a2 = ops.groupnorm_apply(hid, g, st2, *pk[p + ".norm2"], eps=eps, act=ACT_SILU)
         if has_sc:
             res = torch.empty(b, h, w, c_out, device=x.device, dtype=torch.float32)
             ops.conv2d(raw, pk[p + ".conv_shortcut"], out=res)
         else:
             res = x
-        out = hid  # conv2 overwrites the hidden buffer (its 16-bit normalised copy a2 is what conv2 reads)
-        ops.conv2d(a2, pk[p + ".conv2"], out=out, residual=res)
-        return out
+        out = torch.empty(b, h, w, c_out, device=x.device, dtype=torch.float32)
+        out_stats = torch.empty(b, g, 2, device=x.device, dtype=torch.float32) if emit_stats else None
+        ops.conv2d(a2, pk[p + ".conv2"], out=out, residual=res, stats=out_stats, stats_groups=g)
+        return out, out_stats
 
-    def _transformer(self, pk, p, x, enc_kv, kv_len, n_text):
-        """Transformer2DModel + BasicTransformerBlock, transformer_2d.py:255-299, attention.py:276-334."""
+    def _transformer(self, pk, p, x, enc_kv, kv_len, n_text, x_stats=None, emit_stats=False):
+        """Transformer2DModel + BasicTransformerBlock, transformer_2d.py:255-299, attention.py:276-334.
+        Returns (out, GroupNorm moments of out or None)."""
         b, h, w, c = x.shape
         heads, d, inner, dp = pk[p + ".meta"]
         hp = heads * HEAD_PAD
@@ -251,7 +257,7 @@ class UNet2DConditionGuidedModel(PackedModule):
         t = p + ".transformer_blocks.0"
         g = self.config["norm_num_groups"]
         scale = d ** -0.5
-        st = ops.groupnorm_stats(x, g)
+        st = x_stats if x_stats is not None else ops.groupnorm_stats(x, g)
         a = ops.groupnorm_apply(x, g, st, *pk[p + ".norm"], eps=1e-6, act=ACT_NONE)
         y = torch.empty(m, dp, device=dev, dtype=torch.float32)
         ops.linear(a.view(m, c), pk[p + ".proj_in"], out=y)
@@ -279,8 +285,10 @@ class UNet2DConditionGuidedModel(PackedModule):
         y16 = n1  # reuse: [m, dp] 16-bit
         ops.linear(ff, pk[t + ".ff2"], out=y16, residual=y)
         out = torch.empty(b, h, w, c, device=dev, dtype=torch.float32)
-        ops.linear(y16, pk[p + ".proj_out"], out=out.view(m, c), residual=x.view(m, c))
-        return out
+        out_stats = torch.empty(b, g, 2, device=dev, dtype=torch.float32) if emit_stats else None
+        ops.linear(y16, pk[p + ".proj_out"], out=out.view(m, c), residual=x.view(m, c), stats=out_stats, stats_groups=g,
+                   stats_rows_per_img=h * w)
+        return out, out_stats
 
     # ------------------------------------------------------------------ forward
     def forward(self, sample, timestep, guidance, encoder_hidden_states, class_labels=None, timestep_cond=None,
@@ -353,16 +361,19 @@ class UNet2DConditionGuidedModel(PackedModule):
         enc_kv = torch.empty(b, n_text, pk["kv_all"].n, device=dev, dtype=f16)
         ops.linear(enc16.view(b * n_text, -1), pk["kv_all"], out=enc_kv.view(b * n_text, -1))
 
-        # 3. down path
+        # 3. down path.  `st` carries the GroupNorm moments of x whenever the kernel that produced x could emit them
         _, hh, ww, _ = x0.shape
+        g = cfg["norm_num_groups"]
         x = torch.empty(b, hh, ww, cfg["block_out_channels"][0], device=dev, dtype=torch.float32)
-        ops.conv2d(x0, pk["conv_in"], out=x)
+        st = torch.empty(b, g, 2, device=dev, dtype=torch.float32)
+        ops.conv2d(x0, pk["conv_in"], out=x, stats=st, stats_groups=g)
         skips = [x]
         for i in range(4):
             for j in range(2):
-                x = self._resnet(pk, "down_blocks.%d.resnets.%d" % (i, j), x, None, temb_all, eps)
+                x, st = self._resnet(pk, "down_blocks.%d.resnets.%d" % (i, j), x, None, temb_all, eps, st, True)
                 if i < 3:
-                    x = self._transformer(pk, "down_blocks.%d.attentions.%d" % (i, j), x, enc_kv, kv_len, n_text)
+                    x, st = self._transformer(pk, "down_blocks.%d.attentions.%d" % (i, j), x, enc_kv, kv_len, n_text,
+                                              st, True)
                 skips.append(x)
             if i < 3:
                 p = "down_blocks.%d.downsamplers.0.conv" % i
@@ -370,18 +381,22 @@ class UNet2DConditionGuidedModel(PackedModule):
                 x16 = ops.groupnorm_apply(x, 1, None, None, None, act=ACT_NONE)
                 cols = ops.im2col_s2(x16)
                 x = torch.empty(bb, h_ // 2, w_ // 2, c_, device=dev, dtype=torch.float32)
-                ops.linear(cols, pk[p], out=x.view(-1, c_))
+                st = torch.empty(b, g, 2, device=dev, dtype=torch.float32)
+                ops.linear(cols, pk[p], out=x.view(-1, c_), stats=st, stats_groups=g,
+                           stats_rows_per_img=(h_ // 2) * (w_ // 2))
                 skips.append(x)
         # 4. mid
-        x = self._resnet(pk, "mid_block.resnets.0", x, None, temb_all, eps)
-        x = self._transformer(pk, "mid_block.attentions.0", x, enc_kv, kv_len, n_text)
-        x = self._resnet(pk, "mid_block.resnets.1", x, None, temb_all, eps)
-        # 5. up path
+        x, st = self._resnet(pk, "mid_block.resnets.0", x, None, temb_all, eps, st, True)
+        x, st = self._transformer(pk, "mid_block.attentions.0", x, enc_kv, kv_len, n_text, st, True)
+        x, st = self._resnet(pk, "mid_block.resnets.1", x, None, temb_all, eps, st, False)
+        # 5. up path (the resnets normalise torch.cat([x, skip]): their moments come from the stand-alone kernel)
         for i in range(4):
             for j in range(3):
-                x = self._resnet(pk, "up_blocks.%d.resnets.%d" % (i, j), x, skips.pop(), temb_all, eps)
+                last = i == 3 and j == 2
+                x, st = self._resnet(pk, "up_blocks.%d.resnets.%d" % (i, j), x, skips.pop(), temb_all, eps, None, i > 0)
                 if i > 0:
-                    x = self._transformer(pk, "up_blocks.%d.attentions.%d" % (i, j), x, enc_kv, kv_len, n_text)
+                    x, st = self._transformer(pk, "up_blocks.%d.attentions.%d" % (i, j), x, enc_kv, kv_len, n_text, st,
+                                              last)
             if i < 3:
                 p = "up_blocks.%d.upsamplers.0.conv" % i
                 bb, h_, w_, c_ = x.shape
@@ -389,8 +404,8 @@ class UNet2DConditionGuidedModel(PackedModule):
                 x = torch.empty(bb, 2 * h_, 2 * w_, c_, device=dev, dtype=torch.float32)
                 ops.conv2d(up, pk[p], out=x)
         # 6. out
-        g = cfg["norm_num_groups"]
-        st = ops.groupnorm_stats(x, g)
+        if st is None:
+            st = ops.groupnorm_stats(x, g)
         a = ops.groupnorm_apply(x, g, st, *pk["conv_norm_out"], eps=eps, act=ACT_SILU)
         out = torch.empty(b, x.shape[1], x.shape[2], cfg["out_channels"], device=dev, dtype=torch.float32)
         ops.conv2d(a, pk["conv_out"], out=out)

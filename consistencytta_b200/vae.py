@@ -129,37 +129,40 @@ class Decoder(PackedModule):
                     pk[name] = (w.float().contiguous(), sd[name + ".bias"].float().contiguous())
         return pk
 
-    def _resnet(self, pk, p, x):
-        """ResnetBlock.forward (temb None), modules.py:155-175."""
+    def _resnet(self, pk, p, x, x_stats):
+        """ResnetBlock.forward (temb None), modules.py:155-175.  x_stats: GroupNorm moments of x emitted by the kernel
+        that wrote x.  Returns (out, moments of out)."""
         b, h, w, cin = x.shape
         dev = x.device
         has_sc = (p + ".nin_shortcut") in pk
-        st = ops.groupnorm_stats(x, GROUPS)
         raw = torch.empty(b, h, w, cin, device=dev, dtype=ops.OPERAND_DTYPE) if has_sc else None
-        a = ops.groupnorm_apply(x, GROUPS, st, *pk[p + ".norm1"], eps=EPS, act=ACT_SILU, raw_out=raw)
+        a = ops.groupnorm_apply(x, GROUPS, x_stats, *pk[p + ".norm1"], eps=EPS, act=ACT_SILU, raw_out=raw)
         cout = pk[p + ".conv1"].n
-        hid = torch.empty(b, h, w, cout, device=dev, dtype=torch.float32)
-        ops.conv2d(a, pk[p + ".conv1"], out=hid)
+        # 16-bit hidden tensor (only GroupNorm 2 reads it); its moments come out of the conv epilogue
+        hid = torch.empty(b, h, w, cout, device=dev, dtype=ops.OPERAND_DTYPE)
+        st2 = torch.empty(b, GROUPS, 2, device=dev, dtype=torch.float32)
+        ops.conv2d(a, pk[p + ".conv1"], out=hid, stats=st2, stats_groups=GROUPS)
         del a
-        st2 = ops.groupnorm_stats(hid, GROUPS)
         a2 = ops.groupnorm_apply(hid, GROUPS, st2, *pk[p + ".norm2"], eps=EPS, act=ACT_SILU)
+        del hid
         if has_sc:
             res = torch.empty(b, h, w, cout, device=dev, dtype=torch.float32)
             ops.conv2d(raw, pk[p + ".nin_shortcut"], out=res)
         else:
             res = x
-        ops.conv2d(a2, pk[p + ".conv2"], out=hid, residual=res)
-        return hid
+        out = torch.empty(b, h, w, cout, device=dev, dtype=torch.float32)
+        out_stats = torch.empty(b, GROUPS, 2, device=dev, dtype=torch.float32)
+        ops.conv2d(a2, pk[p + ".conv2"], out=out, residual=res, stats=out_stats, stats_groups=GROUPS)
+        return out, out_stats
 
-    def _attn(self, pk, p, x):
+    def _attn(self, pk, p, x, x_stats):
         """AttnBlock.forward, modules.py:204-230: single head over H*W tokens, d = C = 512.
         scores and P.V run on the tcgen05 GEMM per sample; V's bias is added after P.V (softmax rows sum to 1)."""
         b, h, w, c = x.shape
         dev = x.device
         f16 = ops.OPERAND_DTYPE
         n = h * w
-        st = ops.groupnorm_stats(x, GROUPS)
-        a = ops.groupnorm_apply(x, GROUPS, st, *pk[p + ".norm"], eps=EPS, act=ACT_NONE).view(b, n, c)
+        a = ops.groupnorm_apply(x, GROUPS, x_stats, *pk[p + ".norm"], eps=EPS, act=ACT_NONE).view(b, n, c)
         q = torch.empty(b, n, c, device=dev, dtype=f16)
         k = torch.empty(b, n, c, device=dev, dtype=f16)
         ops.linear(a.view(b * n, c), pk[p + ".q"], out=q.view(b * n, c))
@@ -176,8 +179,10 @@ class Decoder(PackedModule):
             ops.softmax_rows(s, float(c) ** -0.5, out=pr)
             ops.linear(pr, ops.PackedWeight(vt, wv.bias, 1, n, c, [0], [0]), out=o[i])
         out = torch.empty(b, h, w, c, device=dev, dtype=torch.float32)
-        ops.linear(o.view(b * n, c), pk[p + ".proj_out"], out=out.view(b * n, c), residual=x.view(b * n, c))
-        return out
+        out_stats = torch.empty(b, GROUPS, 2, device=dev, dtype=torch.float32)
+        ops.linear(o.view(b * n, c), pk[p + ".proj_out"], out=out.view(b * n, c), residual=x.view(b * n, c),
+                   stats=out_stats, stats_groups=GROUPS, stats_rows_per_img=n)
+        return out, out_stats
 
     def forward_nhwc(self, z16, out16=None):
         """z16: 16-bit channels-last [B, 256, 16, 8] (after post_quant_conv) -> fp32 [B, 1024, 64, 1]."""
@@ -185,21 +190,22 @@ class Decoder(PackedModule):
         dev = z16.device
         b, h, w, _ = z16.shape
         x = torch.empty(b, h, w, pk["conv_in"].n, device=dev, dtype=torch.float32)
-        ops.conv2d(z16, pk["conv_in"], out=x)
-        x = self._resnet(pk, "mid.block_1", x)
-        x = self._attn(pk, "mid.attn_1", x)
-        x = self._resnet(pk, "mid.block_2", x)
+        st = torch.empty(b, GROUPS, 2, device=dev, dtype=torch.float32)
+        ops.conv2d(z16, pk["conv_in"], out=x, stats=st, stats_groups=GROUPS)
+        x, st = self._resnet(pk, "mid.block_1", x, st)
+        x, st = self._attn(pk, "mid.attn_1", x, st)
+        x, st = self._resnet(pk, "mid.block_2", x, st)
         for lvl in (2, 1, 0):
             for blk in range(3):
-                x = self._resnet(pk, "up.%d.block.%d" % (lvl, blk), x)
+                x, st = self._resnet(pk, "up.%d.block.%d" % (lvl, blk), x, st)
             if lvl != 0:  # Upsample, modules.py:53-57
                 bb, hh, ww, cc = x.shape
                 up = ops.groupnorm_apply(x, 1, None, None, None, act=ACT_NONE, upsample=True)
                 del x
                 x = torch.empty(bb, 2 * hh, 2 * ww, cc, device=dev, dtype=torch.float32)
-                ops.conv2d(up, pk["up.%d.upsample.conv" % lvl], out=x)
+                st = torch.empty(b, GROUPS, 2, device=dev, dtype=torch.float32)
+                ops.conv2d(up, pk["up.%d.upsample.conv" % lvl], out=x, stats=st, stats_groups=GROUPS)
                 del up
-        st = ops.groupnorm_stats(x, GROUPS)
         a = ops.groupnorm_apply(x, GROUPS, st, *pk["norm_out"], eps=EPS, act=ACT_SILU)
         bb, hh, ww, _ = x.shape
         del x

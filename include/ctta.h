@@ -59,6 +59,7 @@ long long ctta_launch_count(void);
  *     v   = act(acc + bias[n] + rowadd[img(m), n])
  *     v   = (v + residual[orow(m), n]) * out_scale
  *     out[orow(m), n] = v (+ out[orow(m), n] if accumulate) ;   out2[orow(m), n] = f16/bf16( act2(v) )   (optional)
+ *     stats[img(m), group(n)] += (v, v^2)                                                              (optional)
  * Replaces, in the reference: F.conv2d 3x3/1x1 (diffusers/models/resnet.py:570,590,593,157;
  * unet_2d_condition_guided.py:863,940; audioldm/variational_autoencoder/modules.py:56,159,167,173,207-209,228,
  * 658,680; autoencoder.py:99), F.linear (attention_processor.py:1110-1135; transformer_2d.py:267,295;
@@ -108,6 +109,14 @@ typedef struct {
   int32_t out_rows_per_img;
   int32_t out_stride;
   int32_t out_off;
+  /* ---- optional fused GroupNorm moments of the result v (the value written to out): stats[img, g, 0] += sum v,
+   *      stats[img, g, 1] += sum v^2 over the n / stats_groups channels of group g and all rows of image img
+   *      (the statistics pass of the FOLLOWING F.group_norm: resnet.py:555,581, modules.py:38-41).  Zeroed here.
+   *      Needs the TMA epilogue (n >= 32, aligned pitches), out_stride == 1, channels per group a power of two >= 4;
+   *      ROWS mode: image = row / stats_rows_per_img (a multiple of 32).  Returns CTTA_ERR_UNSUPPORTED otherwise. */
+  float* stats;
+  int32_t stats_groups;
+  int32_t stats_rows_per_img;
 } ctta_gemm_desc;
 
 int ctta_gemm(const ctta_gemm_desc* desc, void* stream);

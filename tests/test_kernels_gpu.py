@@ -60,7 +60,10 @@ def test_linear_geglu():
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 16, 64, 128), (3, 256, 16, 8, 256), (1, 64, 4, 192, 8),
-                                            (5, 32, 2, 128, 64), (1, 128, 64, 128, 1), (2, 16, 32, 320, 512)])
+                                            (5, 32, 2, 128, 64), (1, 128, 64, 128, 1), (2, 16, 32, 320, 512),
+                                            # large enough for M super-tiles in stream mode (>= 2 x 148 tiles of 256 pixels)
+                                            (24, 256, 16, 64, 96), (2, 1024, 64, 128, 128), (40, 128, 8, 72, 256),
+                                            (70, 64, 4, 128, 64), (3, 512, 32, 256, 512)])
 def test_conv2d_3x3(n, h, w, cin, cout):
     torch.manual_seed(2)
     x = r16(torch.randn(n, cin, h, w, device=DEV))
@@ -95,10 +98,12 @@ def test_conv2d_1x1_residual_out2():
     assert rel(out2, F.silu(ref)) < 1e-3
 
 
-@pytest.mark.parametrize("k,dil,c,t", [(3, 1, 64, 300), (7, 3, 128, 5121), (11, 5, 32, 1000), (7, 1, 64, 129)])
-def test_conv1d(k, dil, c, t):
+@pytest.mark.parametrize("k,dil,c,t,bsz", [(3, 1, 64, 300, 2), (7, 3, 128, 5121, 2), (11, 5, 32, 1000, 2), (7, 1, 64, 129, 2),
+                                           # stream mode with M super-tiles (weights streamed, halo'd activation boxes)
+                                           (11, 5, 128, 40968, 3), (7, 3, 256, 20484, 4), (3, 1, 512, 5121, 16),
+                                           (11, 1, 256, 700, 2)])
+def test_conv1d(k, dil, c, t, bsz):
     torch.manual_seed(4)
-    bsz = 2
     x = r16(torch.randn(bsz, c, t, device=DEV))
     wt = r16(torch.randn(c, c, k, device=DEV) / math.sqrt(k * c))
     b = torch.randn(c, device=DEV)
@@ -126,11 +131,11 @@ def test_conv1d(k, dil, c, t):
     assert rel(y16, F.leaky_relu(out, 0.01)) < 1e-3
 
 
-@pytest.mark.parametrize("k,s,cin,cout,t", [(16, 5, 128, 64, 50), (16, 4, 64, 32, 131), (8, 2, 64, 64, 200),
-                                            (4, 2, 64, 32, 257)])
-def test_conv_transpose1d(k, s, cin, cout, t):
+@pytest.mark.parametrize("k,s,cin,cout,t,bsz", [(16, 5, 128, 64, 50, 2), (16, 4, 64, 32, 131, 2), (8, 2, 64, 64, 200, 2),
+                                                (4, 2, 64, 32, 257, 2), (16, 5, 1024, 512, 1024, 8),
+                                                (16, 4, 512, 256, 5121, 8), (8, 2, 256, 128, 20484, 6)])
+def test_conv_transpose1d(k, s, cin, cout, t, bsz):
     torch.manual_seed(5)
-    bsz = 2
     p = (k - s) // 2
     x = r16(torch.randn(bsz, cin, t, device=DEV))
     wt = r16(torch.randn(cin, cout, k, device=DEV) / math.sqrt(k * cin))
@@ -144,6 +149,62 @@ def test_conv_transpose1d(k, s, cin, cout, t):
     ops.conv_transpose1d(a, phases, t_out, out=out)
     assert not torch.isnan(out).any()
     assert rel(out.permute(0, 2, 1), ref) < 2e-5
+
+
+def _moments(y_nhwc, groups):
+    """y [N, ..., C] fp32 -> [N, groups, 2] (sum, sum of squares) in float64."""
+    n, c = y_nhwc.shape[0], y_nhwc.shape[-1]
+    yg = y_nhwc.double().reshape(n, -1, groups, c // groups)
+    return torch.stack([yg.sum(dim=(1, 3)), (yg * yg).sum(dim=(1, 3))], dim=-1)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,out16", [(3, 64, 16, 64, 128, False), (2, 128, 8, 32, 256, True),
+                                                  (5, 32, 2, 128, 512, False), (2, 256, 16, 64, 1024, True),
+                                                  (24, 256, 16, 64, 128, True)])
+def test_conv2d_fused_groupnorm_moments(n, h, w, cin, cout, out16):
+    """The conv epilogue accumulates the next GroupNorm's (sum, sum^2) per (image, group): channels per group 4..32,
+    fp32 and 16-bit outputs, with the time-embedding row add and a residual in the value being measured."""
+    torch.manual_seed(21)
+    g = 32
+    x = r16(torch.randn(n, h, w, cin, device=DEV))
+    wt = r16(torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(9 * cin))
+    b = torch.randn(cout, device=DEV)
+    temb = torch.randn(n, cout, device=DEV)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), wt, b, padding=1).permute(0, 2, 3, 1) + temb[:, None, None, :]
+    pw = ops.pack_conv2d(wt, b)
+    stats = torch.full((n, g, 2), float("nan"), device=DEV)
+    if out16:
+        out = torch.empty(n, h, w, cout, device=DEV, dtype=DT)
+        ops.conv2d(x.to(DT), pw, out=out, rowadd=temb, rowadd_rows=h * w, stats=stats, stats_groups=g)
+    else:
+        res = torch.randn(n, h, w, cout, device=DEV)
+        ref = ref + res
+        out = torch.empty(n, h, w, cout, device=DEV)
+        ops.conv2d(x.to(DT), pw, out=out, rowadd=temb, rowadd_rows=h * w, residual=res, stats=stats, stats_groups=g)
+    assert rel(out, ref) < (1e-3 if out16 else 2e-5)
+    want = _moments(ref, g)
+    assert rel(stats, want.float()) < 1e-4
+    # and they normalise like F.group_norm
+    gam, bet = torch.randn(cout, device=DEV), torch.randn(cout, device=DEV)
+    y = ops.groupnorm_apply(out, g, stats, gam, bet, eps=1e-5, act=ops.ACT_SILU)
+    yref = F.silu(F.group_norm(ref.permute(0, 3, 1, 2), g, gam, bet, 1e-5)).permute(0, 2, 3, 1)
+    assert rel(y, yref) < (3e-3 if out16 else 1.5e-3)
+
+
+def test_linear_fused_groupnorm_moments():
+    """ROWS mode: image = row / rows_per_image (transformer proj_out, stride-2 downsampler GEMM); ragged last tile."""
+    torch.manual_seed(22)
+    n_img, hw, k, c, g = 5, 96, 320, 256, 32
+    a = r16(torch.randn(n_img * hw, k, device=DEV))
+    wt = r16(torch.randn(c, k, device=DEV) / math.sqrt(k))
+    b = torch.randn(c, device=DEV)
+    res = torch.randn(n_img * hw, c, device=DEV)
+    ref = a @ wt.t() + b + res
+    stats = torch.empty(n_img, g, 2, device=DEV)
+    out = torch.empty(n_img * hw, c, device=DEV)
+    ops.linear(a.to(DT), ops.pack_linear(wt, b), out=out, residual=res, stats=stats, stats_groups=g, stats_rows_per_img=hw)
+    assert rel(out, ref) < 2e-5
+    assert rel(stats, _moments(ref.view(n_img, hw, c), g).float()) < 1e-4
 
 
 def test_im2col_s2_conv():
