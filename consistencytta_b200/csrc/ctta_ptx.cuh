@@ -169,6 +169,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// The same descriptor split in two 32-bit words, so that an issue loop only ADDS to the low word (start address in
+// 16-byte units: +2 per 16-element K slice, +8 per 128-byte row, + stage pitch / 16 per pipeline stage).
+constexpr uint32_t kUmmaDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo) {
+  return (static_cast<uint64_t>(kUmmaDescHiSw128) << 32) | lo;
+}
 // Same, for an operand whose first row is NOT on a 1024-byte boundary (a row-shifted view of a resident tile):
 // bits [49,52) "matrix base offset" = (start address >> 7) & 7, the row phase inside the 8-row swizzle pattern.
 __device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t smem_addr) {

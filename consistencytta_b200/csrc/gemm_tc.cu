@@ -369,6 +369,32 @@ __device__ __forceinline__ void stats_chunk(const float* v, bool row_valid, int 
   if (low == 0 && g < groups) atomicAdd(dst + 2 * g + (idx & 1), r);
 }
 
+// KK tcgen05.mma of one 64-wide K chunk; descriptors advance by 2 (x16 B) per 16-element K slice.
+template <int KK>
+__device__ __forceinline__ void umma_chunk(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int kk = 0; kk < KK; ++kk)
+    umma_f16(d_tmem, umma_desc_from_lo(a_lo + 2 * kk), umma_desc_from_lo(b_lo + 2 * kk), idesc, kk == 0 ? acc_first : 1u);
+}
+__device__ __forceinline__ void umma_chunk_n(int nkk, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t acc_first) {
+  switch (nkk) {
+    case 1: umma_chunk<1>(d_tmem, a_lo, b_lo, idesc, acc_first); break;
+    case 2: umma_chunk<2>(d_tmem, a_lo, b_lo, idesc, acc_first); break;
+    case 3: umma_chunk<3>(d_tmem, a_lo, b_lo, idesc, acc_first); break;
+    default: umma_chunk<4>(d_tmem, a_lo, b_lo, idesc, acc_first); break;
+  }
+}
+// all taps of one resident-weight (halo mode) sub-tile: tap j = row-shifted view of the activation box
+template <int KK>
+__device__ __forceinline__ void umma_halo_taps(const GemmKParams& p, uint32_t d_tmem, uint32_t a_lo0, uint32_t b_lo0,
+                                               uint32_t b_step, uint32_t idesc) {
+  for (int j = 0; j < p.ntaps; ++j) {
+    const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(p.tap_rows[j]) * 8u;
+    umma_chunk<KK>(d_tmem, a_lo, b_lo0 + j * b_step, idesc, j != 0 ? 1u : 0u);
+  }
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -537,16 +563,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int j = p.grp_first[g]; j < j1; ++j) {
               mbar_wait(smem_u32(&bar_full[w_stage]), w_phase);
               tc_fence_after();
-              const uint32_t b_addr = w_base + static_cast<uint32_t>(w_stage * p.w_stage_bytes);
-              const uint32_t a_tap = a_base + static_cast<uint32_t>(p.tap_rows[j]) * 128u;
-              for (int sub = 0; sub < p.sub_tiles; ++sub) {
-                const uint32_t a_addr = a_tap + static_cast<uint32_t>(sub * kBlockM * 128);
-#pragma unroll
-                for (int kk = 0; kk < kBlockK / 16; ++kk) {
-                  if (kk < nkk)
-                    umma_f16(d_tmem + sub * p.block_n, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32),
-                             idesc, (started | kk) != 0 ? 1u : 0u);
-                }
+              const uint32_t b_lo = umma_desc_lo(w_base + static_cast<uint32_t>(w_stage * p.w_stage_bytes));
+              const uint32_t a_lo = umma_desc_lo(a_base) + static_cast<uint32_t>(p.tap_rows[j]) * 8u;
+              if (nkk == kBlockK / 16) {
+                for (int sub = 0; sub < p.sub_tiles; ++sub)
+                  umma_chunk<4>(d_tmem + sub * p.block_n, a_lo + sub * (kBlockM * 8), b_lo, idesc, started);
+              } else {
+                for (int sub = 0; sub < p.sub_tiles; ++sub)
+                  umma_chunk_n(nkk, d_tmem + sub * p.block_n, a_lo + sub * (kBlockM * 8), b_lo, idesc, started);
               }
               started = 1;
               umma_commit(smem_u32(&bar_empty[w_stage]));
@@ -579,14 +603,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride + sub * p.block_n);
           const uint32_t a_base = stages_base + static_cast<uint32_t>(stage * p.stage_bytes);
-          for (int j = 0; j < p.ntaps; ++j) {
-            // tap j = the resident box shifted by (d_j - min_shift) rows of 128 bytes.  The swizzle phase is taken
-            // from the shared-memory address bits, so a row-shifted start needs no descriptor base offset.
-            const uint32_t a_addr = a_base + static_cast<uint32_t>((p.tap_d0[j] - p.halo_min_shift) * 128);
-            const uint32_t b_addr = tiles_base + static_cast<uint32_t>(j * p.block_n * 128);
-            for (int kk = 0; kk < p.kk_last; ++kk) {
-              umma_f16(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), idesc,
-                       (j | kk) != 0 ? 1u : 0u);
+          // tap j = the resident box shifted by tap_rows[j] rows of 128 bytes.  The swizzle phase is taken from the
+          // shared-memory address bits, so a row-shifted start needs no descriptor base offset.
+          {
+            const uint32_t a_lo0 = umma_desc_lo(a_base), b_lo0 = umma_desc_lo(tiles_base);
+            const uint32_t b_step = static_cast<uint32_t>(p.block_n) * 8u;
+            switch (p.kk_last) {
+              case 1: umma_halo_taps<1>(p, d_tmem, a_lo0, b_lo0, b_step, idesc); break;
+              case 2: umma_halo_taps<2>(p, d_tmem, a_lo0, b_lo0, b_step, idesc); break;
+              case 3: umma_halo_taps<3>(p, d_tmem, a_lo0, b_lo0, b_step, idesc); break;
+              default: umma_halo_taps<4>(p, d_tmem, a_lo0, b_lo0, b_step, idesc); break;
             }
           }
           umma_commit(smem_u32(&bar_empty[stage]));
@@ -613,15 +639,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = 0; kb < k_iters; ++kb) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
           tc_fence_after();
-          const uint32_t a_addr = stages_base + static_cast<uint32_t>(stage * p.stage_bytes);
-          const uint32_t b_addr = a_addr + kATileBytes;
-          const int nkk = (kc == p.k_chunks - 1) ? p.kk_last : kBlockK / 16;  // skip all-zero K slices
-#pragma unroll
-          for (int kk = 0; kk < kBlockK / 16; ++kk) {
-            if (kk < nkk)
-              umma_f16(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), idesc,
-                       (kb | kk) != 0 ? 1u : 0u);
-          }
+          const uint32_t a_lo = umma_desc_lo(stages_base + static_cast<uint32_t>(stage * p.stage_bytes));
+          const uint32_t b_lo = a_lo + (kATileBytes >> 4);
+          if (kc != p.k_chunks - 1 || p.kk_last == kBlockK / 16)
+            umma_chunk<4>(d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
+          else
+            umma_chunk_n(p.kk_last, d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);  // skip all-zero K slices
           umma_commit(smem_u32(&bar_empty[stage]));  // frees the smem stage once these MMAs retire
           if (++kc == p.k_chunks) kc = 0;
           if (++stage == p.n_stages) {
@@ -812,7 +835,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int wrow = q * 32;
     const int wrow_in_img = wrow % p.out_rows_tile_img;
     const int wimg = wrow / p.out_rows_tile_img;
-    int pending_slot = -1;  // ring slot whose TMA store may still be reading shared memory
     uint32_t my_ctr = 0;    // chunks processed by this warp (staging buffer parity)
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -1013,18 +1035,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           fence_proxy_async();
           __syncwarp();
           if (leader) {
+            // the fp32 store is its own bulk group so that its ring slot can be handed back to the loader warp as soon
+            // as the TMA unit has read it (a slot held until the NEXT chunk leaves the loader no room to run ahead
+            // and exposes the residual's load latency once per chunk); the 16-bit staging stays double buffered
             if (out_f32) {
               const uint32_t src = ring_base + first_slot * kRingSlotBytes + wrow * 128;
               if (p.accumulate) tma_reduce_add_3d(&tmap_out, src, col, st_row, st_img);  // out += tile
               else tma_store_3d(&tmap_out, src, col, st_row, st_img);
+              tma_store_commit();
             }
-            if (out_16) tma_store_3d(&tmap_out, st16, col, st_row, st_img);
-            if (has_out2) tma_store_3d(&tmap_out2, st16, col, st_row, st_img);
-            tma_store_commit();
-            tma_store_wait_read<1>();  // everything but the group just committed has finished reading smem
-            if (pending_slot >= 0) mbar_arrive(smem_u32(&bar_ring_empty[pending_slot]));
+            if (out_16 || has_out2) {
+              if (out_16) tma_store_3d(&tmap_out, st16, col, st_row, st_img);
+              if (has_out2) tma_store_3d(&tmap_out2, st16, col, st_row, st_img);
+              tma_store_commit();
+              tma_store_wait_read<1>();  // everything but the 16-bit group just committed has finished reading smem
+            } else {
+              tma_store_wait_read<0>();
+            }
+            if (out_f32) mbar_arrive(smem_u32(&bar_ring_empty[first_slot]));
           }
-          pending_slot = out_f32 ? first_slot : -1;
           __syncwarp();
         }
         // advance (sub, ch) to this group's next chunk
@@ -1207,6 +1236,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
       p.halo = 1;
       p.halo_rows = halo_rows;
       p.halo_min_shift = min_shift;
+      for (int j = 0; j < d->ntaps; ++j) p.tap_rows[j] = static_cast<short>(p.tap_d0[j] - min_shift);
       p.w_bytes = w_bytes;
       p.tiles_off = (w_bytes + 1023) / 1024 * 1024;
       p.stage_bytes = (halo_rows * 128 + 1023) / 1024 * 1024;
@@ -1293,9 +1323,12 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   // ---- stream mode (see GemmKParams::stream): multi-tap convolutions whose epilogue can go through TMA
   p.sub_tiles = 1;
   if (tma_ok && !p.halo && d->ntaps > 1 && d->a_mode != CTTA_A_ROWS && getenv("CTTA_NO_STREAM") == nullptr) {
-    int st = 512 / block_n;            // sub-tiles sharing one weight chunk; all accumulators must fit 512 TMEM columns
+    // sub-tiles sharing one weight chunk: two accumulator stages of st * block_n columns must fit the 512 TMEM
+    // columns so that the epilogue of one tile overlaps the MMAs of the next (N = 256 keeps st = 1)
+    int st = 256 / block_n;
     if (st > 4) st = 4;
-    if (block_n > 128 && st > 2) st = 2;
+    if (st < 1) st = 1;
+    if (getenv("CTTA_STREAM_ST")) st = atoi(getenv("CTTA_STREAM_ST"));
     bool ok = false;
     int box_rows = 0, a_loads = 1, a_stage = 0, box_h = 0;
     if (d->a_mode == CTTA_A_CONV1D) {
@@ -1366,7 +1399,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     // shared-memory feasibility: 2 A stages + 2 weight stages + the smallest epilogue plan
     const int w_stage = block_n * 128;
     const bool f32o = d->out && d->out_dtype == CTTA_F32;
-    const int min_epi = ((f32o || d->residual) ? 2 * kRingSlotBytes : 0) +
+    const int min_epi = ((f32o || d->residual) ? 3 * kRingSlotBytes : 0) +
                         (((d->out && !f32o) || d->out2) ? 4 * 2 * kStage16Bytes : 0) + kBiasBytes;
     if (ok && 2 * a_stage + 2 * w_stage + min_epi <= kSmemBudget) {
       p.stream = 1;
@@ -1499,9 +1532,9 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
         const int st = budget / p.stage_bytes;
         if (st >= 3 || groups == 1) stages = st;
       } else {
-        // a slot that is also a TMA-store source is released one chunk late by each warp group
-        const int need = (out_f32 ? groups + 1 : 2) * p.ring_per_chunk;
-        const int prefs[3] = {need > 4 ? need : 4, need > 3 ? need : 3, need};
+        // every warp group holds one slot while it works on a chunk; the rest is the loader's prefetch distance
+        const int need = 2 * p.ring_per_chunk;
+        const int prefs[3] = {need > 5 ? need : 5, need > 4 ? need : 4, need > 3 ? need : 3};
         for (int i = 0; i < 3 && stages == 0; ++i) {
           const int st = (budget - prefs[i] * kRingSlotBytes) / p.stage_bytes;
           if (st >= 3 || (groups == 1 && i == 2 && st >= 2)) {
