@@ -25,6 +25,7 @@ class GemmDesc(C.Structure):
         ("out2", C.c_void_p), ("out2_ld", C.c_int32), ("act2", C.c_int32), ("act2_slope", C.c_float),
         ("out_rows_per_img", C.c_int32), ("out_stride", C.c_int32), ("out_off", C.c_int32),
         ("stats", C.c_void_p), ("stats_groups", C.c_int32), ("stats_rows_per_img", C.c_int32),
+        ("res_neg_scale", C.c_float),
     ]
 
 
@@ -51,6 +52,7 @@ SIGNATURES = {
     "ctta_wave_to_int16": (C.c_int, [_P, _I64, _P, _P, _P]),
     "ctta_lrelu_cast": (C.c_int, [_P, _I64, _F, _P, _I32, _P]),
     "ctta_cfg_mix": (C.c_int, [_P, _I64, _F, _P, _P]),
+    "ctta_mrf_combine": (C.c_int, [C.POINTER(C.c_void_p), _I32, _I64, _I32, _F, _F, _F, _P, _P]),
 }
 
 _lib = None

@@ -45,12 +45,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug must trap (-> CUDA error on the host) instead of hanging the GPU box.
+// Bounded wait: a protocol bug must trap (-> CUDA error on the host) instead of hanging the GPU box.  The bound is
+// 20 s of WALL time (%globaltimer), so a kernel that is merely time-sliced out on a shared host does not trap.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s at 2 GHz
+    if ((++spins & 0xFFFu) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ULL) __trap();
+    }
   }
 }
 

@@ -301,6 +301,80 @@ extern "C" int ctta_lrelu_cast(const float* x, int64_t numel, float slope, void*
   return 0;
 }
 
+namespace ctta {
+struct MrfPtrs {
+  const uint4* x[4];
+};
+__device__ __forceinline__ void mrf_unpack8(const uint4& u, int is_bf16, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (is_bf16) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    } else {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+}
+// 8 elements per thread per input (16-byte loads), all inputs in flight before the first use
+__global__ void __launch_bounds__(256) mrf_combine_kernel(MrfPtrs in, int n_in, long long nvec, int is_bf16, float in_inv,
+                                                          float out_scale, float out_slope, uint4* __restrict__ y) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < n_in) u[k] = __ldg(in.x[k] + i);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < n_in) {
+        float f[8];
+        mrf_unpack8(u[k], is_bf16, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j] < 0.f ? f[j] * in_inv : f[j];
+      }
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = acc[2 * j] * out_scale, b = acc[2 * j + 1] * out_scale;
+      a = a < 0.f ? a * out_slope : a;
+      b = b < 0.f ? b * out_slope : b;
+      if (is_bf16) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+      } else {
+        const __half2 h = __floats2half2_rn(a, b);
+        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    }
+    y[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+}  // namespace ctta
+
+extern "C" int ctta_mrf_combine(const void* const* x, int32_t n_in, int64_t numel, int32_t dtype, float in_slope,
+                                float out_scale, float out_slope, void* y, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  CTTA_REQUIRE(x && y && n_in >= 1 && n_in <= 4 && numel > 0 && numel % 8 == 0, "mrf_combine: need 1..4 inputs, numel %% 8 == 0");
+  CTTA_REQUIRE(dtype == CTTA_F16 || dtype == CTTA_BF16, "mrf_combine: 16-bit tensors only");
+  CTTA_REQUIRE(in_slope > 0.f, "mrf_combine: in_slope must be positive");
+  ctta::MrfPtrs in{};
+  for (int k = 0; k < n_in; ++k) {
+    CTTA_REQUIRE(x[k] && (reinterpret_cast<uintptr_t>(x[k]) & 15) == 0, "mrf_combine: inputs must be 16-byte aligned");
+    in.x[k] = reinterpret_cast<const uint4*>(x[k]);
+  }
+  CTTA_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "mrf_combine: output must be 16-byte aligned");
+  ctta::mrf_combine_kernel<<<ctta::grid_for(numel / 8, 256 * 2), 256, 0, stream>>>(
+      in, n_in, numel / 8, dtype == CTTA_BF16, 1.f / in_slope, out_scale, out_slope, reinterpret_cast<uint4*>(y));
+  CTTA_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int ctta_cfg_mix(const float* x, int64_t half_numel, float s, float* y, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   CTTA_REQUIRE(x && y && half_numel > 0, "cfg_mix: bad arguments");

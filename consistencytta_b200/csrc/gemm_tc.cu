@@ -36,7 +36,7 @@ constexpr int kSmemBudget = kSmemMaxDynamic - 1024;  // minus alignment slack
 constexpr int kEpiWarp0 = 3;                         // first of the 4 epilogue math warps
 constexpr int kChunkCols = 32;                       // accumulator columns per epilogue chunk
 constexpr int kRingSlotBytes = kBlockM * kChunkCols * 4;  // 16 KiB: 128 rows x 32 fp32 columns (128-B swizzle)
-constexpr int kMaxRing = 6;
+constexpr int kMaxRing = 8;
 constexpr int kStage16Bytes = 32 * kChunkCols * 2;   // 2 KiB: 32 rows x 32 16-bit columns per warp per buffer
 constexpr int kEpiWarps = 8;                         // two warps per TMEM lane quarter, alternating chunks
 constexpr int kBiasBytes = 2 * 256 * 4;
@@ -89,6 +89,10 @@ struct GemmKParams {
   // fused GroupNorm moments of the OUTPUT (sum, sum of squares per (image, group)), accumulated with atomics
   float* stats;
   int stats_groups, stats_cpg, stats_rows;   // channels per group (power of two >= 4); logical rows per image
+  // 16-bit residual (same dtype as the operands): ring slots are 128 rows x 64 B; negative residual values are scaled by
+  // res_neg_scale before the add (inverse LeakyReLU when the residual is given as its LeakyReLU'ed copy)
+  int res16, ring_slot_bytes;
+  float res_neg_scale;
   int acc_single;          // 1: one accumulator stage (sub_tiles * block_n * 2 > 512 TMEM columns), else two
   // stream mode (multi-tap convolutions): per (channel chunk, tap group) ONE halo'd activation box is loaded into
   // the A ring and every tap of the group is a row-shifted UMMA view of it; weight chunks stream through their own
@@ -143,6 +147,24 @@ __device__ __forceinline__ float act_apply(float v, int act, float slope) {
   }
 }
 __device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
+// Exact-erf GELU at half the instructions of erff(): erfc(a) = 2^q(a) on a = |g| / sqrt(2) in [0, 4.4] with a degree-6
+// polynomial q (least squares on Chebyshev nodes of log2 erfc), Phi(g) = 1 - erfc/2 (g >= 0) or erfc/2 (g < 0).
+// Against the float64 erf GELU: max abs error 8.6e-6, max relative error 6e-5 — an order of magnitude under the
+// 16-bit rounding of the value it produces.  Used by the GEGLU epilogue, where erff() made the epilogue ALU-bound.
+__device__ __forceinline__ float gelu_fast(float g) {
+  float a = fminf(fabsf(g) * 0.70710678f, 4.4f);
+  float q = 1.7291631e-04f;
+  q = fmaf(q, a, -3.3274852e-03f);
+  q = fmaf(q, a, 2.8219042e-02f);
+  q = fmaf(q, a, -1.4366551e-01f);
+  q = fmaf(q, a, -9.2350090e-01f);
+  q = fmaf(q, a, -1.6263064e+00f);
+  q = fmaf(q, a, -7.6538774e-05f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  const float h = 0.5f * e;
+  return g * (g >= 0.f ? 1.f - h : h);
+}
 
 __device__ __forceinline__ float ld16(const void* p, int is_bf16, long long i) {
   return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
@@ -231,7 +253,7 @@ __device__ __forceinline__ void epilogue8(const GemmKParams& p, float* v, int co
         float f[8];
         unpack16x8(u, p.res_dtype == CTTA_BF16, f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += f[i];
+        for (int i = 0; i < 8; ++i) v[i] += f[i] < 0.f ? f[i] * p.res_neg_scale : f[i];
       }
     }
     const long long ooff = orow * p.out_ld + col;
@@ -289,8 +311,10 @@ __device__ __forceinline__ void epilogue8(const GemmKParams& p, float* v, int co
     x = act_apply(x, p.act, p.act_slope);
     if (p.residual) {
       const long long off = orow * p.res_ld + c;
-      x += p.res_dtype == CTTA_F32 ? reinterpret_cast<const float*>(p.residual)[off]
-                                   : ld16(p.residual, p.res_dtype == CTTA_BF16, off);
+      float r = p.res_dtype == CTTA_F32 ? reinterpret_cast<const float*>(p.residual)[off]
+                                        : ld16(p.residual, p.res_dtype == CTTA_BF16, off);
+      if (p.res_dtype != CTTA_F32 && r < 0.f) r *= p.res_neg_scale;
+      x += r;
     }
     const long long ooff = orow * p.out_ld + c;
     x *= p.out_scale;
@@ -714,13 +738,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_wait(smem_u32(&bar_ring_empty[slot]), phase ^ 1u);
             const uint32_t full = smem_u32(&bar_ring_full[slot]);
             if (k < p.ring_in) {
-              mbar_arrive_expect_tx(full, kRingSlotBytes);
+              mbar_arrive_expect_tx(full, static_cast<uint32_t>(p.ring_slot_bytes));
               // the fp32 residual tile: one {32 cols x 32 rows} box per epilogue warp (the box shape the stores use)
               const void* map = static_cast<const void*>(&tmap_res);
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq) {
                 const int wr = qq * 32;
-                tma_load_3d(ring_base + slot * kRingSlotBytes + wr * 128, map, full, col,
+                tma_load_3d(ring_base + slot * p.ring_slot_bytes + wr * (p.res16 ? 64 : 128), map, full, col,
                             srow0 + (wr % p.out_rows_tile_img), img0 + wr / p.out_rows_tile_img);
               }
             } else {
@@ -924,8 +948,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t w[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float o0 = v[4 * i + 0] * gelu_erf(v[4 * i + 1]) * p.out_scale;
-            const float o1 = v[4 * i + 2] * gelu_erf(v[4 * i + 3]) * p.out_scale;
+            const float o0 = v[4 * i + 0] * gelu_fast(v[4 * i + 1]) * p.out_scale;
+            const float o1 = v[4 * i + 2] * gelu_fast(v[4 * i + 3]) * p.out_scale;
             w[i] = (generic && p.out_dtype == CTTA_BF16) ? pack16(o0, o1, 1) : pack_f16_sat(o0, o1);
           }
           const uint32_t dst = st16 + lane * 32;
@@ -954,12 +978,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const int slot = static_cast<int>(sidx % p.ring_slots);
               const uint32_t ring_phase = static_cast<uint32_t>((sidx / p.ring_slots) & 1);
               mbar_wait(smem_u32(&bar_ring_full[slot]), ring_phase);
-              const uint32_t sa = ring_base + slot * kRingSlotBytes + lr * 128;
+              const uint32_t sa = ring_base + slot * p.ring_slot_bytes + lr * 128;
               if (k == 0) {
                 slot_addr = sa;
                 first_slot = slot;
               }
-              if (k < ring_in) {
+              if (k < ring_in && p.res16) {
+                // 16-bit residual tile: rows of 64 B, 64-byte swizzle (the pattern of the TMA box that wrote it)
+                const uint32_t sa16 = ring_base + slot * p.ring_slot_bytes + lr * 64;
+                const int s3 = (lane >> 1) & 3;
+                const float ns = p.res_neg_scale;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  uint4 u4;
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                               : "=r"(u4.x), "=r"(u4.y), "=r"(u4.z), "=r"(u4.w)
+                               : "r"(sa16 + ((g ^ s3) << 4)));
+                  float f8[8];
+                  unpack16x8(u4, p.is_bf16, f8);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[8 * g + i] += f8[i] < 0.f ? f8[i] * ns : f8[i];
+                }
+              } else if (k < ring_in) {
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                   float4 r4;
@@ -1039,7 +1079,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // as the TMA unit has read it (a slot held until the NEXT chunk leaves the loader no room to run ahead
             // and exposes the residual's load latency once per chunk); the 16-bit staging stays double buffered
             if (out_f32) {
-              const uint32_t src = ring_base + first_slot * kRingSlotBytes + wrow * 128;
+              const uint32_t src = ring_base + first_slot * p.ring_slot_bytes + wrow * 128;
               if (p.accumulate) tma_reduce_add_3d(&tmap_out, src, col, st_row, st_img);  // out += tile
               else tma_store_3d(&tmap_out, src, col, st_row, st_img);
               tma_store_commit();
@@ -1282,6 +1322,8 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   p.act = d->act;
   p.act_slope = d->act_slope;
   p.residual = d->residual;
+  p.res_neg_scale = d->res_neg_scale != 0.f ? d->res_neg_scale : 1.f;
+  p.ring_slot_bytes = kRingSlotBytes;
   p.res_dtype = d->res_dtype;
   p.res_ld = d->res_ld;
   p.accumulate = d->accumulate;
@@ -1313,8 +1355,11 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   bool tma_ok = d->n >= 32 && block_n % kChunkCols == 0;
   if (d->out && ((static_cast<long long>(d->out_ld) * out_esz) % 16 || !aligned16(d->out))) tma_ok = false;
   if (d->out2 && ((static_cast<long long>(d->out2_ld) * 2) % 16 || !aligned16(d->out2))) tma_ok = false;
-  if (d->residual && (d->res_dtype != CTTA_F32 || (static_cast<long long>(d->res_ld) * 4) % 16 || !aligned16(d->residual)))
-    tma_ok = false;
+  const bool res16 = d->residual && d->res_dtype != CTTA_F32;
+  if (d->residual && !res16 && ((static_cast<long long>(d->res_ld) * 4) % 16 || !aligned16(d->residual))) tma_ok = false;
+  if (res16 && (d->res_dtype != d->ab_dtype || (static_cast<long long>(d->res_ld) * 2) % 16 || !aligned16(d->residual) ||
+                (d->out && d->out_dtype == CTTA_F32)))
+    tma_ok = false;  // a 16-bit residual tile cannot double as the fp32 staging slot
   if (d->out && d->out_dtype != CTTA_F32 && d->out2) tma_ok = false;
   if (d->accumulate && d->out_dtype != CTTA_F32) tma_ok = false;
   if (d->act == CTTA_ACT_GEGLU && d->out_dtype == CTTA_F32) tma_ok = false;
@@ -1512,10 +1557,15 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
       if (rc) return rc;
     }
     if (d->residual) {
-      int rc = make_row_tmap(&tmap_res, CTTA_F32, d->residual, d->res_ld, d->n, first_row, d->out_stride, n_rows,
-                             d->out_rows_per_img, d->n_img, kChunkCols, CU_TENSOR_MAP_SWIZZLE_128B);
+      int rc = make_row_tmap(&tmap_res, res16 ? d->res_dtype : CTTA_F32, d->residual, d->res_ld, d->n, first_row,
+                             d->out_stride, n_rows, d->out_rows_per_img, d->n_img, kChunkCols,
+                             res16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
+    p.res16 = res16 ? 1 : 0;
+    p.res_neg_scale = d->res_neg_scale != 0.f ? d->res_neg_scale : 1.f;
+    const int slot_b = res16 ? kRingSlotBytes / 2 : kRingSlotBytes;
+    p.ring_slot_bytes = slot_b;
     p.ring_in = d->residual ? 1 : 0;
     const bool out_f32 = d->out && d->out_dtype == CTTA_F32;
     const bool use_ring = out_f32 || p.ring_in > 0;
@@ -1536,7 +1586,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
         const int need = 2 * p.ring_per_chunk;
         const int prefs[3] = {need > 5 ? need : 5, need > 4 ? need : 4, need > 3 ? need : 3};
         for (int i = 0; i < 3 && stages == 0; ++i) {
-          const int st = (budget - prefs[i] * kRingSlotBytes) / p.stage_bytes;
+          const int st = (budget - prefs[i] * slot_b) / p.stage_bytes;
           if (st >= 3 || (groups == 1 && i == 2 && st >= 2)) {
             stages = st;
             ring = prefs[i];
@@ -1552,13 +1602,13 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     CTTA_REQUIRE(stages >= 2, "ctta_gemm: shared-memory plan failed (block_n=%d, stages=%d)", block_n, stages);
     if (use_ring) {
       // leftover room extends the ring
-      int extra = (budget - stages * p.stage_bytes - ring * kRingSlotBytes) / kRingSlotBytes;
+      int extra = (budget - stages * p.stage_bytes - ring * slot_b) / slot_b;
       ring += extra;
       if (ring > kMaxRing) ring = kMaxRing;
     }
     p.n_stages = stages;
     p.ring_slots = ring;
-    ring_bytes = ring * kRingSlotBytes;
+    ring_bytes = ring * slot_b;
     p.ring_off = p.tiles_off + stages * p.stage_bytes;
     p.stage16_off = p.ring_off + ring_bytes;
     p.bias_off = p.stage16_off + st16_bytes;
@@ -1583,6 +1633,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   static const Variant variants[] = {
       {N_, 0, 0, 0, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 0, 0, 0, 1, L_>>},  // conv -> lrelu'ed 16-bit operand
       {N_, 0, 1, 1, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 1, 1, 0, 1, L_>>},  // + residual, fp32 stream + operand
+      {N_, 0, 1, 0, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 1, 0, 0, 1, L_>>},  // + 16-bit residual -> lrelu'ed operand
       {N_, 0, 0, 1, 0, 1, L_, gemm_tc_kernel<EpiCfg<N_, 0, 0, 1, 0, 1, L_>>},  // transposed conv
       {N_, 0, 1, 1, 0, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 1, 1, 0, 0, N_>>},  // fp32 out + residual
       {N_, 1, 0, 1, 0, 0, N_, gemm_tc_kernel<EpiCfg<N_, 1, 0, 1, 0, 0, N_>>},  // fp32 out + time embedding

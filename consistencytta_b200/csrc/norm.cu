@@ -85,9 +85,9 @@ __global__ void __launch_bounds__(256) gn_moments_kernel(const void* __restrict_
 
 // ---------------------------------------------------------------------------------------------- GN apply
 // One item = (pixel, 8-channel vector): 32 B (fp32) or 16 B (16-bit) in, 16 B out.  Each thread keeps kGnItems items in
-// flight (all loads issued before any use) so a resident SM has >= 100 KB of reads outstanding; 32-bit index math.
+// flight (all loads issued before any use; 2 items for fp32 input, 4 for 16-bit input = 64 B per thread) so a
+// resident SM has >= 100 KB of reads outstanding; 32-bit index math.
 // grid (blocks, n_img).
-constexpr int kGnItems = 2;
 
 struct Vec8 {
   float v[8];
@@ -139,6 +139,7 @@ __device__ __forceinline__ void store8(void* base, int dtype, long long elem_off
   }
 }
 
+template <int kGnItems>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ x, int x_dtype, int c, int ld,
                                                        const void* __restrict__ x2, int c2, int ld2, int h, int w,
                                                        int groups, const float* __restrict__ stats,
@@ -359,13 +360,18 @@ extern "C" int ctta_groupnorm_apply(const void* x, int32_t x_dtype, int32_t c, i
   CTTA_REQUIRE(!(raw_out && upsample2x), "groupnorm_apply: raw_out and upsample are exclusive");
   CTTA_REQUIRE(act == CTTA_ACT_NONE || act == CTTA_ACT_SILU, "groupnorm_apply: act must be NONE or SILU");
   const long long total = static_cast<long long>(h) * w * ((c + c2) / 8);
-  long long blocks = (total + 256 * kGnItems - 1) / (256 * kGnItems);
+  const int items = x_dtype == CTTA_F32 ? 2 : 4;
+  long long blocks = (total + 256 * items - 1) / (256 * items);
   const long long cap = (static_cast<long long>(sm_count()) * 32 + n_img - 1) / n_img;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   dim3 grid(static_cast<unsigned>(blocks), n_img);
-  gn_apply_kernel<<<grid, 256, 0, stream>>>(x, x_dtype, c, ld, x2, c2, ld2, h, w, groups, stats, gamma, beta,
-                                            eps, act, upsample2x, y, y_dtype, y_ld, raw_out, raw_ld);
+  if (items == 2)
+    gn_apply_kernel<2><<<grid, 256, 0, stream>>>(x, x_dtype, c, ld, x2, c2, ld2, h, w, groups, stats, gamma, beta,
+                                                 eps, act, upsample2x, y, y_dtype, y_ld, raw_out, raw_ld);
+  else
+    gn_apply_kernel<4><<<grid, 256, 0, stream>>>(x, x_dtype, c, ld, x2, c2, ld2, h, w, groups, stats, gamma, beta,
+                                                 eps, act, upsample2x, y, y_dtype, y_ld, raw_out, raw_ld);
   CTTA_LAUNCH_CHECK();
   return 0;
 }

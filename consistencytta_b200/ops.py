@@ -139,9 +139,11 @@ def pack_conv_transpose1d(weight, bias, stride, padding, dtype=None):
 def gemm(a, pw, mode=A_ROWS, n_img=1, h=1, w=None, rows_per_img=None, a_ld=None, out=None, out_ld=None,
          out_rows_per_img=None, residual=None, res_ld=None, rowadd=None, rowadd_rows=1, act=ACT_NONE, act_slope=0.0,
          accumulate=False, out_scale=1.0, out2=None, out2_ld=None, act2=ACT_NONE, act2_slope=0.0, use_bias=True,
-         stats=None, stats_groups=32, stats_rows_per_img=0):
+         stats=None, stats_groups=32, stats_rows_per_img=0, res_neg_scale=1.0):
     """Launches ctta_gemm.  `a` is a 16-bit channels-last tensor; shapes are given explicitly by the caller.
-    `stats` (fp32 [n_img, stats_groups, 2]) receives the GroupNorm moments of the result (fused statistics pass)."""
+    `stats` (fp32 [n_img, stats_groups, 2]) receives the GroupNorm moments of the result (fused statistics pass).
+    A 16-bit `residual` may be the LeakyReLU'ed copy of the true residual: negative values are multiplied by
+    `res_neg_scale` (= 1 / slope) before the add."""
     _require_cuda(a)
     d = GemmDesc()
     d.a = a.data_ptr()
@@ -173,6 +175,7 @@ def gemm(a, pw, mode=A_ROWS, n_img=1, h=1, w=None, rows_per_img=None, a_ld=None,
         d.residual = residual.data_ptr()
         d.res_dtype = _DT[residual.dtype]
         d.res_ld = res_ld if res_ld is not None else residual.shape[-1]
+        d.res_neg_scale = res_neg_scale
     d.accumulate = 1 if accumulate else 0
     d.out_scale = out_scale
     if out is not None:
@@ -358,6 +361,20 @@ def lrelu_cast(x, slope, out=None):
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=OPERAND_DTYPE)
     check(lib().ctta_lrelu_cast(_ptr(x), x.numel(), slope, _ptr(out), _DT[out.dtype], _stream()))
+    return out
+
+
+def mrf_combine(xs, in_slope, out_scale, out_slope, out=None):
+    """HiFi-GAN MRF sum over the LeakyReLU'ed 16-bit ResBlock outputs `xs` -> LeakyReLU'ed 16-bit operand of the next stage."""
+    x0 = xs[0]
+    _require_cuda(x0)
+    if out is None:
+        out = torch.empty_like(x0)
+    ptrs = (C.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+    for x in xs:
+        assert x.shape == x0.shape and x.dtype == x0.dtype and x.is_contiguous()
+    check(lib().ctta_mrf_combine(ptrs, len(xs), x0.numel(), _DT[x0.dtype], in_slope, out_scale, out_slope, _ptr(out),
+                                 _stream()))
     return out
 
 

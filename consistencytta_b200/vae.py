@@ -55,8 +55,11 @@ class Generator(PackedModule):
     def forward_btc(self, mel16):
         """mel16: 16-bit channels-last [B, T, 64] -> fp32 waveform [B, T_out].
 
-        Every LeakyReLU / residual add / MRF sum / divide-by-3 / tanh of models.py:56-63,101-117 is a GEMM epilogue:
-        convs emit the fp32 residual stream plus the LeakyReLU'ed 16-bit operand of the next conv."""
+        Every activation of models.py:56-63,101-117 lives in HBM only as its LeakyReLU'ed 16-bit copy lx = lrelu(x, 0.1):
+        it is the operand of the next conv AND (LeakyReLU being invertible: x = lx >= 0 ? lx : 10 lx) the residual of
+        the ResBlock add, which the conv epilogue undoes on load.  So a ResBlock pair costs 2+2 (c1) + 2+2+2 (c2) bytes
+        per element instead of 16 with a separate fp32 residual stream, and the MRF sum / divide-by-3 / next LeakyReLU is
+        one pass over the three 16-bit branch outputs."""
         pk = self.packed()
         dev = mel16.device
         f16 = ops.OPERAND_DTYPE
@@ -65,35 +68,28 @@ class Generator(PackedModule):
         cur16 = torch.empty(b, t, c, device=dev, dtype=f16)
         ops.conv1d(mel16, pk["conv_pre"], out2=cur16, act2=ACT_LRELU, act2_slope=0.1)  # models.py:102,104
         nk = self.num_kernels
+        slope = 0.1
         for i, (u, k) in enumerate(zip(self.h["upsample_rates"], self.h["upsample_kernel_sizes"])):
             c //= 2
             t = (t - 1) * u - 2 * ((k - u) // 2) + k
-            x = torch.empty(b, t, c, device=dev, dtype=torch.float32)
-            x16 = torch.empty(b, t, c, device=dev, dtype=f16)
-            ops.conv_transpose1d(cur16, pk["ups.%d" % i], t, out=x, out2=x16, act2=ACT_LRELU, act2_slope=0.1)
-            xs = torch.empty(b, t, c, device=dev, dtype=torch.float32)
-            nxt16 = torch.empty(b, t, c, device=dev, dtype=f16)
+            lx = torch.empty(b, t, c, device=dev, dtype=f16)
+            ops.conv_transpose1d(cur16, pk["ups.%d" % i], t, out2=lx, act2=ACT_LRELU, act2_slope=slope)
             tmp16 = torch.empty(b, t, c, device=dev, dtype=f16)
-            r_a = torch.empty(b, t, c, device=dev, dtype=torch.float32)
-            r_b = torch.empty(b, t, c, device=dev, dtype=torch.float32)
-            r16 = torch.empty(b, t, c, device=dev, dtype=f16)
+            ping = [torch.empty(b, t, c, device=dev, dtype=f16) for _ in range(2)]
+            branch = [torch.empty(b, t, c, device=dev, dtype=f16) for _ in range(nk)]
             last = i == self.num_upsamples - 1
             for j in range(nk):
                 n = i * nk + j
-                res, a16 = x, x16
+                cur = lx
                 for m in range(3):
-                    ops.conv1d(a16, pk["rb.%d.c1.%d" % (n, m)], out2=tmp16, act2=ACT_LRELU, act2_slope=0.1)
-                    if m < 2:
-                        dst = r_a if m == 0 else r_b
-                        ops.conv1d(tmp16, pk["rb.%d.c2.%d" % (n, m)], out=dst, residual=res, out2=r16,
-                                   act2=ACT_LRELU, act2_slope=0.1)
-                        res, a16 = dst, r16
-                    else:
-                        # MRF: x = (sum_j resblock_j(x)) / 3 (models.py:108-112) accumulated in fp32 by the TMA unit
-                        ops.conv1d(tmp16, pk["rb.%d.c2.%d" % (n, m)], out=xs, residual=res, accumulate=j > 0,
-                                   out_scale=1.0 / nk)
-            ops.lrelu_cast(xs, 0.01 if last else 0.1, out=nxt16)  # models.py:104 / :113 (default slope)
-            cur16 = nxt16
+                    ops.conv1d(cur, pk["rb.%d.c1.%d" % (n, m)], out2=tmp16, act2=ACT_LRELU, act2_slope=slope)
+                    dst = branch[j] if m == 2 else ping[m]
+                    # x' = x + c2(lrelu(c1(lrelu(x)))) with x recovered from lrelu(x); emitted again as lrelu(x')
+                    ops.conv1d(tmp16, pk["rb.%d.c2.%d" % (n, m)], residual=cur, res_neg_scale=1.0 / slope, out2=dst,
+                               act2=ACT_LRELU, act2_slope=slope)
+                    cur = dst
+            # x = (sum_j resblock_j(x)) / 3 (models.py:108-112), then LeakyReLU of models.py:104 / :113 (default slope)
+            cur16 = ops.mrf_combine(branch, slope, 1.0 / nk, 0.01 if last else 0.1, out=tmp16)
         wav = torch.empty(b, t, 1, device=dev, dtype=torch.float32)
         ops.conv1d(cur16, pk["conv_post"], out=wav, act=ACT_TANH)  # models.py:113-115
         return wav.view(b, t)

@@ -117,6 +117,10 @@ typedef struct {
   float* stats;
   int32_t stats_groups;
   int32_t stats_rows_per_img;
+  /* ---- 16-bit residual given as its LeakyReLU'ed copy: negative residual values are multiplied by res_neg_scale
+   *      (= 1 / slope) before the add, 0 means 1.  HiFi-GAN's ResBlock x + c2(...) (hifigan/models.py:56-63) reads the
+   *      same 16-bit tensor the previous conv consumed as its operand instead of a separate fp32 residual stream. */
+  float res_neg_scale;
 } ctta_gemm_desc;
 
 int ctta_gemm(const ctta_gemm_desc* desc, void* stream);
@@ -187,6 +191,12 @@ int ctta_wave_to_int16(const float* wav, int64_t numel, const float* minmax, int
 /* y = 16-bit(leaky_relu(x, slope)) elementwise: operand of the next up-sampling stage after the MRF sum
  * (audioldm/hifigan/models.py:104,112-113). */
 int ctta_lrelu_cast(const float* x, int64_t numel, float slope, void* y, int32_t y_dtype, void* stream);
+
+/* HiFi-GAN multi-receptive-field sum (audioldm/hifigan/models.py:106-112 followed by the LeakyReLU at :104 / :113):
+ * the n_in (<= 4) ResBlock outputs arrive as their LeakyReLU'ed 16-bit copies (negative values scaled by in_slope);
+ * y = 16-bit( lrelu( out_scale * sum_i lrelu^-1(x_i), out_slope ) ), the operand of the next up-sampling stage. */
+int ctta_mrf_combine(const void* const* x, int32_t n_in, int64_t numel, int32_t dtype, float in_slope, float out_scale,
+                     float out_slope, void* y, void* stream);
 
 /* (1 - s) * uncond + s * cond on the two batch halves (models/audio_consistency_model.py:453-456). */
 int ctta_cfg_mix(const float* x, int64_t half_numel, float s, float* y, void* stream);

@@ -151,6 +151,38 @@ def test_conv_transpose1d(k, s, cin, cout, t, bsz):
     assert rel(out.permute(0, 2, 1), ref) < 2e-5
 
 
+@pytest.mark.parametrize("k,dil,c,t,bsz", [(3, 1, 32, 1000, 2), (7, 3, 64, 2500, 3), (11, 5, 128, 40968, 3),
+                                           (11, 1, 256, 20484, 4), (7, 1, 512, 5121, 8), (3, 5, 32, 163872, 4)])
+def test_conv1d_lrelu_residual_stream(k, dil, c, t, bsz):
+    """HiFi-GAN ResBlock pair with the activation held only as lx = lrelu(x): c2's epilogue adds the residual recovered
+    from lx (negative values * 1/slope) and emits lrelu(x') again (16-bit residual ring + inverse LeakyReLU)."""
+    torch.manual_seed(31)
+    slope = 0.1
+    x = torch.randn(bsz, t, c, device=DEV)
+    lx = F.leaky_relu(x, slope).to(DT)                       # what lives in HBM
+    a = r16(torch.randn(bsz, t, c, device=DEV))              # lrelu(c1(...)) operand
+    wt = r16(torch.randn(c, c, k, device=DEV) / math.sqrt(k * c))
+    b = torch.randn(c, device=DEV)
+    pw = ops.pack_conv1d(wt, b, dilation=dil)
+    out2 = torch.empty(bsz, t, c, device=DEV, dtype=DT)
+    ops.conv1d(a.to(DT), pw, residual=lx, res_neg_scale=1.0 / slope, out2=out2, act2=ops.ACT_LRELU, act2_slope=slope)
+    lxf = lx.float()
+    x_rec = torch.where(lxf < 0, lxf / slope, lxf)
+    ref = F.conv1d(a.permute(0, 2, 1), wt, b, dilation=dil, padding=(k * dil - dil) // 2).permute(0, 2, 1) + x_rec
+    assert rel(out2, F.leaky_relu(ref, slope)) < 1e-3
+
+
+def test_mrf_combine():
+    torch.manual_seed(32)
+    slope = 0.1
+    xs = [torch.randn(3, 1000, 64, device=DEV) for _ in range(3)]
+    lxs = [F.leaky_relu(x, slope).to(DT) for x in xs]
+    rec = [torch.where(l.float() < 0, l.float() / slope, l.float()) for l in lxs]
+    for out_slope in (0.1, 0.01):
+        y = ops.mrf_combine(lxs, slope, 1.0 / 3, out_slope)
+        assert rel(y, F.leaky_relu(sum(rec) / 3, out_slope)) < 1e-3
+
+
 def _moments(y_nhwc, groups):
     """y [N, ..., C] fp32 -> [N, groups, 2] (sum, sum of squares) in float64."""
     n, c = y_nhwc.shape[0], y_nhwc.shape[-1]
