@@ -25,7 +25,7 @@ class GemmDesc(C.Structure):
         ("out2", C.c_void_p), ("out2_ld", C.c_int32), ("act2", C.c_int32), ("act2_slope", C.c_float),
         ("out_rows_per_img", C.c_int32), ("out_stride", C.c_int32), ("out_off", C.c_int32),
         ("stats", C.c_void_p), ("stats_groups", C.c_int32), ("stats_rows_per_img", C.c_int32),
-        ("res_neg_scale", C.c_float),
+        ("res_neg_scale", C.c_float), ("wgt_img_stride", C.c_int64),
     ]
 
 

@@ -47,7 +47,13 @@ struct Params {
   unsigned short* o;
   long long o_bs, o_ls;
   int is_bf16;
+  long long* dbg;   // optional phase timestamps of CTA 0 / softmax warp 0 (tools/attn_phases.py), else NULL
 };
+#define ATC_STAMP(slot)                                                            \
+  do {                                                                             \
+    if (p.dbg != nullptr && blockIdx.x + blockIdx.y + blockIdx.z == 0 && warp == 0 && lane == 0 && j >= 8 && j < 16) \
+      p.dbg[(j - 8) * 8 + (slot)] = clock64();                                     \
+  } while (0)
 
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
   asm volatile(
@@ -223,8 +229,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     float m_used = -INFINITY, l_sum = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t par = static_cast<uint32_t>(j & 1);
+      ATC_STAMP(0);
       mbar_wait(smem_u32(&bar_s_full[t]), par);
       tc_fence_after();
+      ATC_STAMP(1);
       uint32_t u[128];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) tmem_ld_x32(s_addr + ch * 32, u + ch * 32);
@@ -232,6 +240,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_s_free[t]));
+      ATC_STAMP(2);
       float* s = reinterpret_cast<float*>(u);
       const int valid = kvl - j * kTile;            // keys of this tile below kv_len
       if (valid < kTile) {
@@ -274,6 +283,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
       }
       if (j == 0 && t == 1) mbar_wait(smem_u32(&bar_stagger), 0);   // start half an iteration behind group 0
+      ATC_STAMP(3);
       const float mc = m_used * c;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
@@ -288,11 +298,13 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         l3 += s[i + 3];
       }
       l_sum += (l0 + l1) + (l2 + l3);
+      ATC_STAMP(4);
       if (j == 0 && t == 0) {
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_stagger));
       }
       if (j > 0 && !waited_pv) mbar_wait(smem_u32(&bar_pv_done[t]), par ^ 1u);   // PV(j-1) no longer reads P_t
+      ATC_STAMP(5);
 #pragma unroll
       for (int ck = 0; ck < 16; ++ck) {
         const uint32_t w0 = pack_p(s[8 * ck + 0], s[8 * ck + 1], p.is_bf16);
@@ -306,6 +318,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tc_fence_before();     // orders the O rescale (tcgen05.st) before the arrive
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_p_full[t]));
+      ATC_STAMP(6);
     }
     // ---- epilogue: O_t / l -> 16-bit, this thread's row
     mbar_wait(smem_u32(&bar_pv_done[t]), static_cast<uint32_t>((n_tiles - 1) & 1));
@@ -337,6 +350,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tmem_dealloc(tmem_base, kTmemCols);
   }
 }
+
+}  // namespace atc
+long long* g_attn_dbg = nullptr;
+namespace atc {
 
 static int make_qkv_tmap(CUtensorMap* m, int dtype, const void* ptr, int heads, int len, int batch, long long ls,
                          long long bs) {
@@ -374,6 +391,13 @@ int attention_tc_launch(const void* q, const void* k, const void* v, void* o, in
   p.o_bs = o_bs;
   p.o_ls = o_ls;
   p.is_bf16 = dtype == CTTA_BF16;
+  p.dbg = nullptr;
+  if (getenv("CTTA_ATTN_DEBUG") != nullptr) {
+    static long long* dbg_buf = nullptr;   // debug only: managed memory the tool reads back through ctta_attention_debug
+    if (dbg_buf == nullptr) cudaMallocManaged(&dbg_buf, 64 * sizeof(long long));
+    p.dbg = dbg_buf;
+    g_attn_dbg = dbg_buf;
+  }
   static bool configured = false;
   if (!configured) {
     CTTA_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(flash_attn_tc_kernel),
@@ -387,3 +411,11 @@ int attention_tc_launch(const void* q, const void* k, const void* v, void* o, in
 }
 
 }  // namespace ctta
+
+// debug helper for tools/attn_phases.py: copies the 64 phase timestamps of the last CTTA_ATTN_DEBUG launch
+extern "C" int ctta_attention_debug(long long* host_out) {
+  if (ctta::g_attn_dbg == nullptr) return CTTA_ERR_INVALID;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 64; ++i) host_out[i] = ctta::g_attn_dbg[i];
+  return 0;
+}

@@ -91,6 +91,7 @@ struct GemmKParams {
   int stats_groups, stats_cpg, stats_rows;   // channels per group (power of two >= 4); logical rows per image
   // 16-bit residual (same dtype as the operands): ring slots are 128 rows x 64 B; negative residual values are scaled by
   // res_neg_scale before the add (inverse LeakyReLU when the residual is given as its LeakyReLU'ed copy)
+  int w_batched;           // the W operand has one [n, K] matrix per image (batched GEMM: attention scores / P.V)
   int res16, ring_slot_bytes;
   float res_neg_scale;
   int acc_single;          // 1: one accumulator stage (sub_tiles * block_n * 2 > 512 TMEM columns), else two
@@ -552,7 +553,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               } else {
                 tma_load_4d(a_dst, &tmap_a, full, kc * kBlockK, tc.c1 + d0, tc.c2 + d1, tc.c3);
               }
-              tma_load_2d(b_dst, &tmap_b, full, kb * kBlockK, tc.n0);
+              if (p.w_batched) tma_load_3d(b_dst, &tmap_b, full, kb * kBlockK, tc.n0, tc.c2);
+              else tma_load_2d(b_dst, &tmap_b, full, kb * kBlockK, tc.n0);
               if (++stage == p.n_stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -1307,7 +1309,18 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     int rc = make_tmap(&tmap_a, p.is_bf16, d->a, 4, dims, strides, box);
     if (rc) return rc;
   }
-  {
+  if (d->wgt_img_stride != 0) {
+    // batched GEMM: image i multiplies its own [n, c_pad] matrix (attention scores q.k^T and P.V per sample)
+    CTTA_REQUIRE(d->a_mode == CTTA_A_CONV1D && d->ntaps == 1 && d->wgt_img_stride % 8 == 0 &&
+                     d->wgt_img_stride >= static_cast<long long>(d->n) * c_pad,
+                 "ctta_gemm: per-image weights need CONV1D mode with one tap and a 16-byte aligned image stride");
+    cuuint64_t dims[3] = {(cuuint64_t)c_pad, (cuuint64_t)d->n, (cuuint64_t)d->n_img};
+    cuuint64_t strides[2] = {(cuuint64_t)c_pad * esz, (cuuint64_t)d->wgt_img_stride * esz};
+    cuuint32_t box[3] = {kBlockK, (cuuint32_t)block_n, 1};
+    int rc = make_tmap(&tmap_b, p.is_bf16, d->wgt, 3, dims, strides, box);
+    if (rc) return rc;
+    p.w_batched = 1;
+  } else {
     cuuint64_t dims[2] = {(cuuint64_t)d->ntaps * c_pad, (cuuint64_t)d->n};
     cuuint64_t strides[1] = {(cuuint64_t)d->ntaps * c_pad * esz};
     cuuint32_t box[2] = {kBlockK, (cuuint32_t)block_n};

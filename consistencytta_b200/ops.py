@@ -139,7 +139,7 @@ def pack_conv_transpose1d(weight, bias, stride, padding, dtype=None):
 def gemm(a, pw, mode=A_ROWS, n_img=1, h=1, w=None, rows_per_img=None, a_ld=None, out=None, out_ld=None,
          out_rows_per_img=None, residual=None, res_ld=None, rowadd=None, rowadd_rows=1, act=ACT_NONE, act_slope=0.0,
          accumulate=False, out_scale=1.0, out2=None, out2_ld=None, act2=ACT_NONE, act2_slope=0.0, use_bias=True,
-         stats=None, stats_groups=32, stats_rows_per_img=0, res_neg_scale=1.0):
+         stats=None, stats_groups=32, stats_rows_per_img=0, res_neg_scale=1.0, wgt_img_stride=0):
     """Launches ctta_gemm.  `a` is a 16-bit channels-last tensor; shapes are given explicitly by the caller.
     `stats` (fp32 [n_img, stats_groups, 2]) receives the GroupNorm moments of the result (fused statistics pass).
     A 16-bit `residual` may be the LeakyReLU'ed copy of the true residual: negative values are multiplied by
@@ -190,6 +190,7 @@ def gemm(a, pw, mode=A_ROWS, n_img=1, h=1, w=None, rows_per_img=None, a_ld=None,
     d.out_rows_per_img = out_rows_per_img if out_rows_per_img is not None else rows_per_img
     d.out_stride = pw.out_stride
     d.out_off = pw.out_off
+    d.wgt_img_stride = wgt_img_stride
     if stats is not None:
         d.stats = stats.data_ptr()
         d.stats_groups = stats_groups
@@ -215,6 +216,16 @@ def conv1d(a, pw, rows_per_img=None, out_rows_per_img=None, **kw):
     rp = rows_per_img if rows_per_img is not None else t
     return gemm(a, pw, mode=A_CONV1D, n_img=b, h=1, w=t, rows_per_img=rp,
                 out_rows_per_img=out_rows_per_img if out_rows_per_img is not None else rp, a_ld=a.stride(1), **kw)
+
+
+def bmm_nt(a, b, bias=None, out=None):
+    """Batched out[i] = a[i] @ b[i]^T (+ bias): a [B, M, K], b [B, N, K] 16-bit (K % 64 == 0), out [B, M, N]."""
+    bsz, m, k = a.shape
+    n = b.shape[1]
+    assert b.shape[0] == bsz and b.shape[2] == k and k % 64 == 0 and a.is_contiguous() and b.is_contiguous()
+    pw = PackedWeight(b, bias, 1, k, n, [0], [0])
+    return gemm(a, pw, mode=A_CONV1D, n_img=bsz, h=1, w=m, rows_per_img=m, out_rows_per_img=m, a_ld=k, out=out,
+                wgt_img_stride=n * k)
 
 
 def conv_transpose1d(a, phases, t_out, **kw):

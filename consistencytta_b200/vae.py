@@ -164,16 +164,21 @@ class Decoder(PackedModule):
         ops.linear(a.view(b * n, c), pk[p + ".q"], out=q.view(b * n, c))
         ops.linear(a.view(b * n, c), pk[p + ".k"], out=k.view(b * n, c))
         wv = pk[p + ".v"]
+        # all samples at once (batched GEMMs: image i multiplies its own K-major operand):
+        #   V^T[i] = W_v . a[i]^T,   S[i] = q[i] . k[i]^T (fp32),   P = softmax(S / sqrt(c)),   o[i] = P[i] . V[i] + b_v
+        wv_rep = pk.get((p, "v_rep"))   # W_v replicated per sample: the A operand of the batched V^T GEMM
+        if wv_rep is None or wv_rep.shape[0] != b:
+            wv_rep = pk[(p, "v_rep")] = wv.w.unsqueeze(0).expand(b, c, c).contiguous()
+        vt = torch.empty(b, c, n, device=dev, dtype=f16)
+        ops.bmm_nt(wv_rep, a, out=vt)
+        s = torch.empty(b, n, n, device=dev, dtype=torch.float32)
+        ops.bmm_nt(q, k, out=s)
+        pr = torch.empty(b, n, n, device=dev, dtype=f16)
+        ops.softmax_rows(s.view(b * n, n), float(c) ** -0.5, out=pr.view(b * n, n))
+        del s
         o = torch.empty(b, n, c, device=dev, dtype=f16)
-        s = torch.empty(n, n, device=dev, dtype=torch.float32)
-        pr = torch.empty(n, n, device=dev, dtype=f16)
-        vt = torch.empty(c, n, device=dev, dtype=f16)
-        for i in range(b):
-            # V^T[c, token] = W_v[c, :] . a[token, :]  (a as the K-major "weight" operand)
-            ops.linear(wv.w, ops.PackedWeight(a[i], None, 1, c, n, [0], [0]), out=vt)
-            ops.linear(q[i], ops.PackedWeight(k[i], None, 1, c, n, [0], [0]), out=s)
-            ops.softmax_rows(s, float(c) ** -0.5, out=pr)
-            ops.linear(pr, ops.PackedWeight(vt, wv.bias, 1, n, c, [0], [0]), out=o[i])
+        ops.bmm_nt(pr, vt, bias=wv.bias, out=o)
+        del pr
         out = torch.empty(b, h, w, c, device=dev, dtype=torch.float32)
         out_stats = torch.empty(b, GROUPS, 2, device=dev, dtype=torch.float32)
         ops.linear(o.view(b * n, c), pk[p + ".proj_out"], out=out.view(b * n, c), residual=x.view(b * n, c),

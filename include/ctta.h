@@ -121,6 +121,9 @@ typedef struct {
    *      (= 1 / slope) before the add, 0 means 1.  HiFi-GAN's ResBlock x + c2(...) (hifigan/models.py:56-63) reads the
    *      same 16-bit tensor the previous conv consumed as its operand instead of a separate fp32 residual stream. */
   float res_neg_scale;
+  /* ---- batched GEMM: != 0 gives image i its own weight matrix at wgt + i * wgt_img_stride elements (CONV1D mode, one
+   *      tap, c % 64 == 0): attention scores q.k^T and P.V of the VAE AttnBlock (modules.py:216-225) for all samples. */
+  int64_t wgt_img_stride;
 } ctta_gemm_desc;
 
 int ctta_gemm(const ctta_gemm_desc* desc, void* stream);

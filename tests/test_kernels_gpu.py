@@ -172,6 +172,21 @@ def test_conv1d_lrelu_residual_stream(k, dil, c, t, bsz):
     assert rel(out2, F.leaky_relu(ref, slope)) < 1e-3
 
 
+def test_bmm_nt_batched_weights():
+    """Per-image weight matrices (VAE AttnBlock: q.k^T, P.V, W_v.a^T for every sample in one launch)."""
+    torch.manual_seed(33)
+    bsz, m, n, k = 5, 300, 640, 192
+    a = r16(torch.randn(bsz, m, k, device=DEV))
+    b = r16(torch.randn(bsz, n, k, device=DEV) / math.sqrt(k))
+    bias = torch.randn(n, device=DEV)
+    out = torch.empty(bsz, m, n, device=DEV)
+    ops.bmm_nt(a.to(DT), b.to(DT), bias=bias, out=out)
+    assert rel(out, torch.einsum("bmk,bnk->bmn", a, b) + bias) < 2e-5
+    out16 = torch.empty(bsz, m, n, device=DEV, dtype=DT)
+    ops.bmm_nt(a.to(DT), b.to(DT), out=out16)
+    assert rel(out16, torch.einsum("bmk,bnk->bmn", a, b)) < 1e-3
+
+
 def test_mrf_combine():
     torch.manual_seed(32)
     slope = 0.1
