@@ -116,6 +116,22 @@ __device__ __forceinline__ Vec8 load8(const void* base, int dtype, long long ele
   }
   return r;
 }
+__device__ __forceinline__ Vec8 unpack8(const uint4& u, int dtype) {
+  Vec8 r;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (dtype == CTTA_BF16) {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    } else {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      r.v[2 * i] = t.x;
+      r.v[2 * i + 1] = t.y;
+    }
+  }
+  return r;
+}
 __device__ __forceinline__ uint4 pack8(const Vec8& f, int dtype) {
   uint32_t w[4];
 #pragma unroll
@@ -139,8 +155,8 @@ __device__ __forceinline__ void store8(void* base, int dtype, long long elem_off
   }
 }
 
-template <int kGnItems>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ x, int x_dtype, int c, int ld,
+template <int kGnItems, bool kIn16>
+__global__ void __launch_bounds__(256, kIn16 ? 3 : 5) gn_apply_kernel(const void* __restrict__ x, int x_dtype, int c, int ld,
                                                        const void* __restrict__ x2, int c2, int ld2, int h, int w,
                                                        int groups, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -166,69 +182,77 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
   const unsigned step = gridDim.x * blockDim.x;
   const long long img_row0 = static_cast<long long>(n) * hw;
   for (unsigned base = blockIdx.x * blockDim.x + threadIdx.x; base < total; base += step * kGnItems) {
-    Vec8 f[kGnItems];
-    unsigned pix[kGnItems], ch[kGnItems];
-    bool ok[kGnItems];
+    // 16-bit inputs stay packed (one uint4 per item) until they are processed, so 8 items = 128 B per thread can be
+    // in flight at 4 registers each
+    Vec8 f[kIn16 ? 1 : kGnItems];
+    uint4 r16[kIn16 ? kGnItems : 1];
 #pragma unroll
     for (int k = 0; k < kGnItems; ++k) {
       const unsigned idx = base + k * step;
-      ok[k] = idx < total;
-      pix[k] = idx / nvec;
-      ch[k] = (idx - pix[k] * nvec) << 3;
-      if (ok[k]) {
-        const bool second = ch[k] >= static_cast<unsigned>(c);
-        f[k] = load8(second ? x2 : x, x_dtype,
-                     (img_row0 + pix[k]) * (second ? ld2 : ld) + (second ? ch[k] - c : ch[k]));
+      const unsigned pix_k = idx / nvec;
+      const unsigned ch_k = (idx - pix_k * nvec) << 3;
+      if (idx < total) {
+        const bool second = ch_k >= static_cast<unsigned>(c);
+        const long long off = (img_row0 + pix_k) * (second ? ld2 : ld) + (second ? ch_k - c : ch_k);
+        if (kIn16)
+          r16[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(second ? x2 : x) + off));
+        else
+          f[k] = load8(second ? x2 : x, x_dtype, off);
       }
     }
 #pragma unroll
     for (int k = 0; k < kGnItems; ++k) {
-      if (!ok[k]) continue;
-      if (raw) store8(raw, y_dtype, (img_row0 + pix[k]) * raw_ld + ch[k], f[k]);
+      const unsigned idx = base + k * step;   // (recomputed rather than kept: registers are what limits occupancy)
+      if (idx >= total) continue;
+      const unsigned pix_k = idx / nvec;
+      const unsigned ch_k = (idx - pix_k * nvec) << 3;
+      Vec8& fk = f[kIn16 ? 0 : k];
+      if (kIn16) fk = unpack8(r16[k], x_dtype);
+      if (raw) store8(raw, y_dtype, (img_row0 + pix_k) * raw_ld + ch_k, fk);
       if (stats) {
-        const int g = ch[k] / cpg;  // 8 | cpg is not required: 4 | cpg, so the vector may straddle two groups
-        const int g2 = (ch[k] + 4) / cpg;
+        const int g = ch_k / cpg;  // 8 | cpg is not required: 4 | cpg, so the vector may straddle two groups
+        const int g2 = (ch_k + 4) / cpg;
         const float m0 = s_mean[g], r0 = s_rstd[g], m1 = s_mean[g2], r1 = s_rstd[g2];
-        const float4 ga0 = __ldg(reinterpret_cast<const float4*>(gamma + ch[k]));
-        const float4 ga1 = __ldg(reinterpret_cast<const float4*>(gamma + ch[k]) + 1);
-        const float4 be0 = __ldg(reinterpret_cast<const float4*>(beta + ch[k]));
-        const float4 be1 = __ldg(reinterpret_cast<const float4*>(beta + ch[k]) + 1);
-        f[k].v[0] = (f[k].v[0] - m0) * r0 * ga0.x + be0.x;
-        f[k].v[1] = (f[k].v[1] - m0) * r0 * ga0.y + be0.y;
-        f[k].v[2] = (f[k].v[2] - m0) * r0 * ga0.z + be0.z;
-        f[k].v[3] = (f[k].v[3] - m0) * r0 * ga0.w + be0.w;
-        f[k].v[4] = (f[k].v[4] - m1) * r1 * ga1.x + be1.x;
-        f[k].v[5] = (f[k].v[5] - m1) * r1 * ga1.y + be1.y;
-        f[k].v[6] = (f[k].v[6] - m1) * r1 * ga1.z + be1.z;
-        f[k].v[7] = (f[k].v[7] - m1) * r1 * ga1.w + be1.w;
+        const float4 ga0 = __ldg(reinterpret_cast<const float4*>(gamma + ch_k));
+        const float4 ga1 = __ldg(reinterpret_cast<const float4*>(gamma + ch_k) + 1);
+        const float4 be0 = __ldg(reinterpret_cast<const float4*>(beta + ch_k));
+        const float4 be1 = __ldg(reinterpret_cast<const float4*>(beta + ch_k) + 1);
+        fk.v[0] = (fk.v[0] - m0) * r0 * ga0.x + be0.x;
+        fk.v[1] = (fk.v[1] - m0) * r0 * ga0.y + be0.y;
+        fk.v[2] = (fk.v[2] - m0) * r0 * ga0.z + be0.z;
+        fk.v[3] = (fk.v[3] - m0) * r0 * ga0.w + be0.w;
+        fk.v[4] = (fk.v[4] - m1) * r1 * ga1.x + be1.x;
+        fk.v[5] = (fk.v[5] - m1) * r1 * ga1.y + be1.y;
+        fk.v[6] = (fk.v[6] - m1) * r1 * ga1.z + be1.z;
+        fk.v[7] = (fk.v[7] - m1) * r1 * ga1.w + be1.w;
       }
       if (act == CTTA_ACT_SILU) {
-        if (kGnItems == 4) {
+        if (kIn16) {
           // 16-bit input: 4 B/element of traffic makes two MUFU ops per element (ex2 + rcp) the bound at full HBM
           // speed, so use x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU op; tanh.approx is good to 2^-11
           // relative, the rounding of the 16-bit value written next
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float hx = 0.5f * f[k].v[i];
+            const float hx = 0.5f * fk.v[i];
             float th;
             asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hx));
-            f[k].v[i] = fmaf(hx, th, hx);
+            fk.v[i] = fmaf(hx, th, hx);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[k].v[i] = __fdividef(f[k].v[i], 1.f + __expf(-f[k].v[i]));
+          for (int i = 0; i < 8; ++i) fk.v[i] = __fdividef(fk.v[i], 1.f + __expf(-fk.v[i]));
         }
       }
       if (!up) {
-        store8(y, y_dtype, (img_row0 + pix[k]) * y_ld + ch[k], f[k]);
+        store8(y, y_dtype, (img_row0 + pix_k) * y_ld + ch_k, fk);
       } else {
-        const int ph = pix[k] / w, pw = pix[k] - ph * w;
+        const int ph = pix_k / w, pw = pix_k - ph * w;
         const int w2 = 2 * w;
         const long long o = (static_cast<long long>(n) * 4 * hw + static_cast<long long>(2 * ph) * w2 + 2 * pw);
-        store8(y, y_dtype, o * y_ld + ch[k], f[k]);
-        store8(y, y_dtype, (o + 1) * y_ld + ch[k], f[k]);
-        store8(y, y_dtype, (o + w2) * y_ld + ch[k], f[k]);
-        store8(y, y_dtype, (o + w2 + 1) * y_ld + ch[k], f[k]);
+        store8(y, y_dtype, o * y_ld + ch_k, fk);
+        store8(y, y_dtype, (o + 1) * y_ld + ch_k, fk);
+        store8(y, y_dtype, (o + w2) * y_ld + ch_k, fk);
+        store8(y, y_dtype, (o + w2 + 1) * y_ld + ch_k, fk);
       }
     }
   }
@@ -373,17 +397,17 @@ extern "C" int ctta_groupnorm_apply(const void* x, int32_t x_dtype, int32_t c, i
   CTTA_REQUIRE(!(raw_out && upsample2x), "groupnorm_apply: raw_out and upsample are exclusive");
   CTTA_REQUIRE(act == CTTA_ACT_NONE || act == CTTA_ACT_SILU, "groupnorm_apply: act must be NONE or SILU");
   const long long total = static_cast<long long>(h) * w * ((c + c2) / 8);
-  const int items = x_dtype == CTTA_F32 ? 2 : 4;
+  const int items = x_dtype == CTTA_F32 ? 2 : 8;
   long long blocks = (total + 256 * items - 1) / (256 * items);
   const long long cap = (static_cast<long long>(sm_count()) * 32 + n_img - 1) / n_img;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   dim3 grid(static_cast<unsigned>(blocks), n_img);
   if (items == 2)
-    gn_apply_kernel<2><<<grid, 256, 0, stream>>>(x, x_dtype, c, ld, x2, c2, ld2, h, w, groups, stats, gamma, beta,
+    gn_apply_kernel<2, false><<<grid, 256, 0, stream>>>(x, x_dtype, c, ld, x2, c2, ld2, h, w, groups, stats, gamma, beta,
                                                  eps, act, upsample2x, y, y_dtype, y_ld, raw_out, raw_ld);
   else
-    gn_apply_kernel<4><<<grid, 256, 0, stream>>>(x, x_dtype, c, ld, x2, c2, ld2, h, w, groups, stats, gamma, beta,
+    gn_apply_kernel<8, true><<<grid, 256, 0, stream>>>(x, x_dtype, c, ld, x2, c2, ld2, h, w, groups, stats, gamma, beta,
                                                  eps, act, upsample2x, y, y_dtype, y_ld, raw_out, raw_ld);
   CTTA_LAUNCH_CHECK();
   return 0;
