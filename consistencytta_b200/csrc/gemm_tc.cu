@@ -25,8 +25,6 @@
 
 namespace ctta {
 
-int narrow_conv_launch(const ctta_gemm_desc* d, cudaStream_t stream);   // narrow_conv.cu
-
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                         // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
@@ -1197,11 +1195,6 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
                  "ctta_gemm: GEGLU epilogue supports bias only and needs n %% 8 == 0");
   if (d->accumulate) CTTA_REQUIRE(d->out != nullptr && d->out2 == nullptr, "ctta_gemm: accumulate needs out and excludes out2");
   if (d->rowadd) CTTA_REQUIRE(d->rowadd_rows >= 1, "ctta_gemm: rowadd_rows must be >= 1");
-  if (d->n == 1 && d->ntaps > 1 && getenv("CTTA_NO_NARROW") == nullptr) {
-    // single-output-channel convolutions are channel reductions, not GEMMs: CUDA-core kernel (narrow_conv.cu)
-    const int rc = narrow_conv_launch(d, stream);
-    if (rc <= 0) return rc;
-  }
 
   GemmKParams p{};
   p.a_mode = d->a_mode;
