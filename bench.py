@@ -278,7 +278,7 @@ def main():
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": hib, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands, f32 accumulate/residual", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
             "config": {"workload": ("UNet2DConditionGuidedModel forward only" if args.unet_only else
                                     "full pipeline UNet + AudioLDM VAE decode + HiFi-GAN, 160000-sample 16 kHz output"),
                        "batch_per_gpu": B, "global_batch": clips_per_step, "text_len": L, "guidance": 4.0,

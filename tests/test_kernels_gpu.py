@@ -187,6 +187,31 @@ def test_bmm_nt_batched_weights():
     assert rel(out16, torch.einsum("bmk,bnk->bmn", a, b)) < 1e-3
 
 
+@pytest.mark.parametrize("mode,c,k", [("conv2d", 128, 3), ("conv1d", 32, 7), ("conv1d", 64, 3)])
+def test_single_output_channel_conv(mode, c, k):
+    """n == 1 multi-tap convolutions (VAE conv_out, HiFi-GAN conv_post + tanh) (direct-epilogue tcgen05 path; a CUDA-core reduction kernel was tried and was slower)."""
+    torch.manual_seed(34)
+    if mode == "conv2d":
+        n, h, w = 3, 96, 64
+        x = r16(torch.randn(n, c, h, w, device=DEV))
+        wt = r16(torch.randn(1, c, k, k, device=DEV) / math.sqrt(k * k * c))
+        b = torch.randn(1, device=DEV)
+        ref = F.conv2d(x, wt, b, padding=k // 2).permute(0, 2, 3, 1)
+        out = torch.full((n, h, w, 1), float("nan"), device=DEV)
+        out16 = torch.empty(n, h, w, 1, device=DEV, dtype=DT)
+        ops.conv2d(x.permute(0, 2, 3, 1).contiguous().to(DT), ops.pack_conv2d(wt, b), out=out, out2=out16)
+        assert rel(out, ref) < 2e-5 and rel(out16, ref) < 1e-3
+    else:
+        bsz, t = 3, 5000
+        x = r16(torch.randn(bsz, c, t, device=DEV))
+        wt = r16(torch.randn(1, c, k, device=DEV) / math.sqrt(k * c))
+        b = torch.randn(1, device=DEV)
+        ref = torch.tanh(F.conv1d(x, wt, b, padding=k // 2)).permute(0, 2, 1)
+        out = torch.full((bsz, t, 1), float("nan"), device=DEV)
+        ops.conv1d(x.permute(0, 2, 1).contiguous().to(DT), ops.pack_conv1d(wt, b), out=out, act=ops.ACT_TANH)
+        assert rel(out, ref) < 2e-5
+
+
 def test_mrf_combine():
     torch.manual_seed(32)
     slope = 0.1
