@@ -6,8 +6,9 @@
 // warp 9 = single-thread tcgen05.mma issuer.  The two softmax groups share the SM's MUFU pipes, so group 1 starts half
 // an iteration late: one group's exponentials then overlap the other's TMEM loads / packing / stores.  Per key tile of 128:
 //     S_t   = Q_t K^T            UMMA 128x128x64, fp32 in TMEM (S_t: 128 columns)
-//     P_t   = exp2(c S_t - c m)  softmax warps: tcgen05.ld -> registers -> 16-bit P into swizzled shared memory
-//     O_t  += P_t V              UMMA 128x64x128, V is the MN-major B operand exactly as TMA lands it ([keys, d])
+//     P_t   = exp2(c S_t - c m)  softmax warps: tcgen05.ld -> registers -> packed 16-bit P back into TMEM (tcgen05.st)
+//     O_t  += P_t V              UMMA 128x64x128 with A = P_t from tensor memory; V is the MN-major B operand exactly
+//                                as TMA lands it ([keys, d])
 // The issuer runs QK^T of key tile j+1 as soon as the softmax warps have pulled S(j) into registers, so the tensor
 // core works under the exponentials.  The running max is updated lazily: O_t (in TMEM) is only rescaled when some row
 // of the warp saw its max grow by more than 2^8, which keeps P <= 256 and the result exact (the same stale max is
@@ -35,9 +36,9 @@ constexpr int kLoaderWarp = 8, kMmaWarp = 9;
 constexpr int kSmemQ = 0;
 constexpr int kSmemKV = kSmemQ + 2 * kTileBytes;             // K then V per stage
 constexpr int kSmemP = kSmemKV + kStages * 2 * kTileBytes;   // per query tile: two [128 x 64] K-major halves
-constexpr int kSmemTotal = kSmemP + 2 * 2 * kTileBytes;      // 192 KiB
+constexpr int kSmemTotal = kSmemP;                           // 128 KiB (P lives in tensor memory)
 constexpr int kTmemCols = 512;
-constexpr int kColS = 0, kColO = 256;        // S_t at 128 t, O_t at 256 + 64 t
+constexpr int kColS = 0, kColO = 256, kColP = 384;   // S_t at 128 t, O_t at 256 + 64 t, P_t (16-bit pairs) at 384 + 64 t
 constexpr float kLazyThreshold = 8.f;        // log2 units
 
 struct Params {
@@ -78,6 +79,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]: the 16-bit A operand (P) is read from tensor memory, row = lane, two K elements per
+// 32-bit column (8 columns per 16-wide K slice)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -203,11 +215,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int t = 0; t < 2; ++t) {
           mbar_wait(smem_u32(&bar_p_full[t]), par);     // P_t(j) is in shared memory, O_t rescaled if needed
           tc_fence_after();
-          const uint32_t pa = base + kSmemP + t * 2 * kTileBytes;
 #pragma unroll
           for (int s = 0; s < 8; ++s)
-            umma_f16(tmem_base + kColO + t * kD, umma_desc_sw128(pa + (s >> 2) * kTileBytes + (s & 3) * 32),
-                     umma_desc_sw128_mn(bv + s * 2048), idesc_pv, (j | s) != 0 ? 1u : 0u);
+            umma_f16_ts(tmem_base + kColO + t * kD, tmem_base + kColP + t * 64 + s * 8, umma_desc_sw128_mn(bv + s * 2048),
+                        idesc_pv, (j | s) != 0 ? 1u : 0u);
           umma_commit(smem_u32(&bar_pv_done[t]));
         }
         umma_commit(smem_u32(&bar_kv_empty[stage]));
@@ -223,8 +234,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_addr + kColS + t * kTile;
     const uint32_t o_addr = tmem_base + lane_addr + kColO + t * kD;
-    const uint32_t p_row = base + kSmemP + t * 2 * kTileBytes + row * 128;
-    const int sw = row & 7;
+    const uint32_t p_addr = tmem_base + lane_addr + kColP + t * 64;
     const float c = p.scale_log2;
     float m_used = -INFINITY, l_sum = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
@@ -305,17 +315,18 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       if (j > 0 && !waited_pv) mbar_wait(smem_u32(&bar_pv_done[t]), par ^ 1u);   // PV(j-1) no longer reads P_t
       ATC_STAMP(5);
+      {
+        // P_t -> tensor memory as packed 16-bit pairs (the A operand of the P.V UMMA): row = lane, 64 columns
+        uint32_t w[32];
 #pragma unroll
-      for (int ck = 0; ck < 16; ++ck) {
-        const uint32_t w0 = pack_p(s[8 * ck + 0], s[8 * ck + 1], p.is_bf16);
-        const uint32_t w1 = pack_p(s[8 * ck + 2], s[8 * ck + 3], p.is_bf16);
-        const uint32_t w2 = pack_p(s[8 * ck + 4], s[8 * ck + 5], p.is_bf16);
-        const uint32_t w3 = pack_p(s[8 * ck + 6], s[8 * ck + 7], p.is_bf16);
-        const uint32_t dst = p_row + (ck >> 3) * kTileBytes + (((ck & 7) ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+        for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = pack_p(s[64 * hh + 2 * i], s[64 * hh + 2 * i + 1], p.is_bf16);
+          tmem_st_x32(p_addr + hh * 32, w);
+        }
+        tmem_st_wait();
       }
-      fence_proxy_async();   // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
-      tc_fence_before();     // orders the O rescale (tcgen05.st) before the arrive
+      tc_fence_before();     // orders the P store and the O rescale (tcgen05.st) before the arrive
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_p_full[t]));
       ATC_STAMP(6);
