@@ -42,6 +42,7 @@ SIGNATURES = {
     "ctta_layernorm": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _F, _P, _I32, _I32, _P]),
     "ctta_attention": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I64, _I64, _I64, _I64, _I64,
                                  _I64, _I64, _I64, _P, _F, _P]),
+    "ctta_attention_debug": (C.c_int, [C.POINTER(C.c_longlong)]),
     "ctta_softmax_rows": (C.c_int, [_P, _I32, _I32, _I64, _F, _P, _I32, _I64, _P]),
     "ctta_im2col_s2": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P]),
     "ctta_nchw_to_nhwc": (C.c_int, [_P, _I32, _I32, _I32, _P, _I32, _I32, _F, _P]),

@@ -164,6 +164,11 @@ int ctta_attention(const void* q, const void* k, const void* v, void* o, int32_t
                    int64_t k_bs, int64_t k_ls, int64_t v_bs, int64_t v_ls, int64_t o_bs, int64_t o_ls,
                    const int32_t* kv_len, float scale, void* stream);
 
+/* Debug only: with CTTA_ATTN_DEBUG set in the environment the tcgen05 attention kernel records clock64() at the phase
+ * boundaries of one softmax warp (CTA 0, key tiles 8..15) into managed memory; this copies the 64 stamps to the host
+ * (synchronises the device).  tools/attn_phases.py prints them.  Not used by the product path. */
+int ctta_attention_debug(long long* host_out);
+
 /* y[r, :] = softmax(scale * x[r, :]) for fp32 scores x[rows, ld] -> 16-bit probabilities (VAE AttnBlock,
  * audioldm/variational_autoencoder/modules.py:217-218; scores and P.V run through ctta_gemm). */
 int ctta_softmax_rows(const float* x, int32_t rows, int32_t cols, int64_t ld, float scale, void* y, int32_t y_dtype,
