@@ -26,6 +26,7 @@ class GemmDesc(C.Structure):
         ("out_rows_per_img", C.c_int32), ("out_stride", C.c_int32), ("out_off", C.c_int32),
         ("stats", C.c_void_p), ("stats_groups", C.c_int32), ("stats_rows_per_img", C.c_int32),
         ("res_neg_scale", C.c_float), ("wgt_img_stride", C.c_int64),
+        ("out_up_phase", C.c_int32), ("stats_keep", C.c_int32),
     ]
 
 

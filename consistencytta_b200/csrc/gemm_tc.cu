@@ -91,6 +91,7 @@ struct GemmKParams {
   int stats_groups, stats_cpg, stats_rows;   // channels per group (power of two >= 4); logical rows per image
   // 16-bit residual (same dtype as the operands): ring slots are 128 rows x 64 B; negative residual values are scaled by
   // res_neg_scale before the add (inverse LeakyReLU when the residual is given as its LeakyReLU'ed copy)
+  int out4d;               // upsample-phase output: 4-D TMA map {cols, w, h, img}; store coordinates (col, r % W, r / W, img)
   int w_batched;           // the W operand has one [n, K] matrix per image (batched GEMM: attention scores / P.V)
   int res16, ring_slot_bytes;
   float res_neg_scale;
@@ -1083,6 +1084,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (out_f32) {
               const uint32_t src = ring_base + first_slot * p.ring_slot_bytes + wrow * 128;
               if (p.accumulate) tma_reduce_add_3d(&tmap_out, src, col, st_row, st_img);  // out += tile
+              else if (p.out4d) tma_store_4d(&tmap_out, src, col, st_row % p.W, st_row / p.W, st_img);
               else tma_store_3d(&tmap_out, src, col, st_row, st_img);
               tma_store_commit();
             }
@@ -1246,6 +1248,8 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     if (eff_rows > max_rows) eff_rows = static_cast<int>(max_rows);
   }
   if (eff_rows <= 0) return 0;  // nothing to write
+  if (d->out_up_phase)
+    CTTA_REQUIRE(d->out_stride == 1 && d->out_off == 0, "ctta_gemm: upsample-phase output excludes out_stride / out_off");
   p.rows_per_img = eff_rows;
   for (int j = 0; j < d->ntaps; ++j) {
     p.tap_d0[j] = static_cast<short>(d->tap_d0[j] + q_start);
@@ -1522,7 +1526,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     if (!ok)
       return set_error(CTTA_ERR_UNSUPPORTED, "ctta_gemm: fused GroupNorm moments unsupported for this problem (n=%d groups=%d)",
                        d->n, d->stats_groups);
-    CTTA_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * n_stat_img * d->stats_groups, stream));
+    if (!d->stats_keep) CTTA_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * n_stat_img * d->stats_groups, stream));
     p.stats = d->stats;
     p.stats_groups = d->stats_groups;
     p.stats_cpg = cpg;
@@ -1551,13 +1555,31 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   memset(&tmap_out2, 0, sizeof(tmap_out2));
   memset(&tmap_res, 0, sizeof(tmap_res));
   int ring_bytes = 0, st16_bytes = 0, bias_bytes = 0;
+  if (d->out_up_phase && !tma_ok)
+    return set_error(CTTA_ERR_UNSUPPORTED, "ctta_gemm: upsample-phase output needs the TMA epilogue (n >= 32, aligned pitches)");
   if (tma_ok) {
     // geometry of the row maps (see ctta_gemm_desc: out row = r * out_stride + out_off, dropped outside the image)
     const long long first_row = eff_out_off;
     const long long n_rows = p.rows_per_img;
     p.row_coord_shift = 0;
     const bool geglu = d->act == CTTA_ACT_GEGLU;
-    if (d->out) {
+    if (d->out_up_phase) {
+      // logical pixel (h, w) -> output pixel (2h + ph, 2w + pw): a warp's 32 consecutive pixels are a {wb x 32 / wb} box
+      const int ph = (d->out_up_phase - 1) >> 1, pw = (d->out_up_phase - 1) & 1;
+      const bool ok = d->out_up_phase >= 1 && d->out_up_phase <= 4 && d->a_mode == CTTA_A_CONV2D && p.stream && d->out &&
+                      d->out_dtype == CTTA_F32 && !d->out2 && !d->residual && !d->accumulate &&
+                      (d->w >= 32 ? d->w % 32 == 0 : 32 % d->w == 0);
+      if (!ok) return set_error(CTTA_ERR_UNSUPPORTED, "ctta_gemm: upsample-phase output unsupported for this problem (h=%d w=%d)", d->h, d->w);
+      const int wb = d->w >= 32 ? 32 : d->w;
+      const long long pix = static_cast<long long>(d->out_ld) * 4;   // bytes per output pixel
+      const char* base = reinterpret_cast<const char*>(d->out) + (static_cast<long long>(ph) * 2 * d->w + pw) * pix;
+      cuuint64_t dims[4] = {(cuuint64_t)d->n, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n_img};
+      cuuint64_t strides[3] = {(cuuint64_t)(2 * pix), (cuuint64_t)(4LL * d->w * pix), (cuuint64_t)(4LL * d->w * d->h * pix)};
+      cuuint32_t box[4] = {(cuuint32_t)kChunkCols, (cuuint32_t)wb, (cuuint32_t)(32 / wb), 1};
+      int rc = make_tmap_ex(&tmap_out, CTTA_F32, CU_TENSOR_MAP_SWIZZLE_128B, base, 4, dims, strides, box);
+      if (rc) return rc;
+      p.out4d = 1;
+    } else if (d->out) {
       const bool f32 = d->out_dtype == CTTA_F32;
       int rc = make_row_tmap(&tmap_out, d->out_dtype, d->out, d->out_ld, geglu ? d->n / 2 : d->n, first_row,
                              d->out_stride, n_rows, d->out_rows_per_img, d->n_img, geglu ? 16 : kChunkCols,

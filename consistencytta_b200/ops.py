@@ -106,6 +106,31 @@ def pack_conv2d_im2col(weight, bias=None, dtype=None):
     return PackedWeight(_pack_taps(w_k, dtype), _bias(bias, cout, w.device), 1, kh * kw * cin, cout, [0], [0])
 
 
+def pack_upsample2x_conv2d(weight, bias=None, dtype=None):
+    """nearest-2x upsample followed by a 3x3 'same' conv == four 2x2 convs on the low-resolution input, one per output
+    phase (ph, pw): output row 2h + ph reads low-res rows h + floor((ph + kh - 1) / 2), i.e. {h-1, h} for ph = 0 (kernel
+    rows {0}, {1, 2}) and {h, h+1} for ph = 1 (kernel rows {0, 1}, {2}); the same along the width.  Kernel taps that land
+    on the same low-res pixel are summed.  Returns [(PackedWeight, phase_code)] with phase_code = 1 + 2 ph + pw."""
+    dtype = dtype or OPERAND_DTYPE
+    w = weight.detach().float()
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    rows = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}
+    out = []
+    for ph in (0, 1):
+        for pw_ in (0, 1):
+            taps, d0, d1 = [], [], []
+            for dh, khs in rows[ph]:
+                for dw, kws in rows[pw_]:
+                    taps.append(w[:, :, khs][:, :, :, kws].sum(dim=(2, 3)))   # [cout, cin]
+                    d1.append(dh)
+                    d0.append(dw)
+            w_ntc = torch.stack(taps, dim=1)                                   # [cout, 4, cin]
+            out.append((PackedWeight(_pack_taps(w_ntc, dtype), _bias(bias, cout, w.device), 4, cin, cout, d0, d1),
+                        1 + 2 * ph + pw_))
+    return out
+
+
 def pack_conv1d(weight, bias=None, dilation=1, dtype=None):
     """nn.Conv1d weight [cout, cin, k], stride 1, padding (k*d - d)/2 (hifigan/models.py:16-17)."""
     dtype = dtype or OPERAND_DTYPE
@@ -139,7 +164,8 @@ def pack_conv_transpose1d(weight, bias, stride, padding, dtype=None):
 def gemm(a, pw, mode=A_ROWS, n_img=1, h=1, w=None, rows_per_img=None, a_ld=None, out=None, out_ld=None,
          out_rows_per_img=None, residual=None, res_ld=None, rowadd=None, rowadd_rows=1, act=ACT_NONE, act_slope=0.0,
          accumulate=False, out_scale=1.0, out2=None, out2_ld=None, act2=ACT_NONE, act2_slope=0.0, use_bias=True,
-         stats=None, stats_groups=32, stats_rows_per_img=0, res_neg_scale=1.0, wgt_img_stride=0):
+         stats=None, stats_groups=32, stats_rows_per_img=0, res_neg_scale=1.0, wgt_img_stride=0, out_up_phase=0,
+         stats_keep=False):
     """Launches ctta_gemm.  `a` is a 16-bit channels-last tensor; shapes are given explicitly by the caller.
     `stats` (fp32 [n_img, stats_groups, 2]) receives the GroupNorm moments of the result (fused statistics pass).
     A 16-bit `residual` may be the LeakyReLU'ed copy of the true residual: negative values are multiplied by
@@ -191,6 +217,8 @@ def gemm(a, pw, mode=A_ROWS, n_img=1, h=1, w=None, rows_per_img=None, a_ld=None,
     d.out_stride = pw.out_stride
     d.out_off = pw.out_off
     d.wgt_img_stride = wgt_img_stride
+    d.out_up_phase = out_up_phase
+    d.stats_keep = 1 if stats_keep else 0
     if stats is not None:
         d.stats = stats.data_ptr()
         d.stats_groups = stats_groups
@@ -208,6 +236,21 @@ def conv2d(a, pw, **kw):
     """a: [N, H, W, C] 16-bit channels-last; 'same' conv given by pw's taps."""
     n, h, w, _ = a.shape
     return gemm(a, pw, mode=A_CONV2D, n_img=n, h=h, w=w, rows_per_img=h * w, a_ld=a.stride(2), **kw)
+
+
+def conv2d_upsample2x(a, phases, out, stats=None, stats_groups=32):
+    """a: LOW-resolution 16-bit [N, H, W, C]; out: fp32 [N, 2H, 2W, Cout] = conv3x3(nearest_upsample_2x(a))."""
+    n, h, w, _ = a.shape
+    assert out.shape[1] == 2 * h and out.shape[2] == 2 * w and out.dtype == torch.float32 and out.is_contiguous()
+    for i, (pw, code) in enumerate(phases):
+        gemm(a, pw, mode=A_CONV2D, n_img=n, h=h, w=w, rows_per_img=h * w, a_ld=a.stride(2), out=out,
+             out_rows_per_img=h * w, out_up_phase=code, stats=stats, stats_groups=stats_groups, stats_keep=i > 0)
+    return out
+
+
+def upsample2x_conv_supported(h, w):
+    """The fused path needs the stream mainloop (tiles of full-width rows inside one image) and boxable warps."""
+    return h * w >= 128 and w <= 128 and 128 % w == 0 and (w % 32 == 0 if w >= 32 else 32 % w == 0)
 
 
 def conv1d(a, pw, rows_per_img=None, out_rows_per_img=None, **kw):

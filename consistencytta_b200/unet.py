@@ -207,6 +207,8 @@ class UNet2DConditionGuidedModel(PackedModule):
                     transformer("up_blocks.%d.attentions.%d" % (i, j), rboc[i], rheads[i])
             if i < 3:
                 conv("up_blocks.%d.upsamplers.0.conv" % i)
+                n_ = "up_blocks.%d.upsamplers.0.conv" % i
+                pk[n_ + ".up2x"] = ops.pack_upsample2x_conv2d(sd[n_ + ".weight"], sd[n_ + ".bias"])
         norm("conv_norm_out")
         conv("conv_out")
         pk["temb_all"] = ops.pack_linear(torch.cat(temb_w, 0), torch.cat(temb_b, 0))
@@ -400,9 +402,15 @@ class UNet2DConditionGuidedModel(PackedModule):
             if i < 3:
                 p = "up_blocks.%d.upsamplers.0.conv" % i
                 bb, h_, w_, c_ = x.shape
-                up = ops.groupnorm_apply(x, 1, None, None, None, act=ACT_NONE, upsample=True)
-                x = torch.empty(bb, 2 * h_, 2 * w_, c_, device=dev, dtype=torch.float32)
-                ops.conv2d(up, pk[p], out=x)
+                if ops.upsample2x_conv_supported(h_, w_):
+                    # Upsample2D (resnet.py:126-161): nearest 2x + conv3x3 as four 2x2 phase convs on the low-res tensor
+                    x16 = ops.groupnorm_apply(x, 1, None, None, None, act=ACT_NONE)
+                    x = torch.empty(bb, 2 * h_, 2 * w_, c_, device=dev, dtype=torch.float32)
+                    ops.conv2d_upsample2x(x16, pk[p + ".up2x"], x)
+                else:
+                    up = ops.groupnorm_apply(x, 1, None, None, None, act=ACT_NONE, upsample=True)
+                    x = torch.empty(bb, 2 * h_, 2 * w_, c_, device=dev, dtype=torch.float32)
+                    ops.conv2d(up, pk[p], out=x)
         # 6. out
         if st is None:
             st = ops.groupnorm_stats(x, g)

@@ -124,6 +124,13 @@ typedef struct {
   /* ---- batched GEMM: != 0 gives image i its own weight matrix at wgt + i * wgt_img_stride elements (CONV1D mode, one
    *      tap, c % 64 == 0): attention scores q.k^T and P.V of the VAE AttnBlock (modules.py:216-225) for all samples. */
   int64_t wgt_img_stride;
+  /* ---- nearest-2x-upsample + conv fused as four phase convolutions on the LOW-resolution input (resnet.py:146-157,
+   *      modules.py:53-57): out_up_phase = 1 + 2 * ph + pw writes logical pixel (h, w) of image i to output pixel
+   *      (2h + ph, 2w + pw) of an [n_img, 2h, 2w, out_ld] tensor (CONV2D mode, fp32 out, TMA epilogue); 0 = off.
+   *      The 3x3 kernel collapses to 2x2 taps per phase (ops.pack_upsample2x_conv2d): 4/9 of the FLOPs and no
+   *      materialised upsampled operand.  stats_keep != 0 accumulates into `stats` without zeroing it first. */
+  int32_t out_up_phase;
+  int32_t stats_keep;
 } ctta_gemm_desc;
 
 int ctta_gemm(const ctta_gemm_desc* desc, void* stream);

@@ -212,6 +212,25 @@ def test_single_output_channel_conv(mode, c, k):
         assert rel(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize("n,h,w,c,cout", [(2, 256, 16, 64, 128), (2, 64, 4, 96, 256), (3, 128, 8, 64, 64),
+                                          (2, 512, 32, 64, 96), (1, 128, 64, 32, 32)])
+def test_upsample2x_conv_phases(n, h, w, c, cout):
+    """nearest-2x upsample + conv3x3 as four 2x2 phase convs on the low-resolution input, with fused GroupNorm moments."""
+    torch.manual_seed(35)
+    x = r16(torch.randn(n, c, h, w, device=DEV))
+    wt = r16(torch.randn(cout, c, 3, 3, device=DEV) / math.sqrt(9 * c))
+    b = torch.randn(cout, device=DEV)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), wt, b, padding=1).permute(0, 2, 3, 1)
+    phases = ops.pack_upsample2x_conv2d(wt, b)
+    out = torch.full((n, 2 * h, 2 * w, cout), float("nan"), device=DEV)
+    stats = torch.full((n, 32, 2), float("nan"), device=DEV)
+    assert ops.upsample2x_conv_supported(h, w)
+    ops.conv2d_upsample2x(x.permute(0, 2, 3, 1).contiguous().to(DT), phases, out, stats=stats, stats_groups=32)
+    assert not torch.isnan(out).any()
+    assert rel(out, ref) < 1e-3      # summed taps are rounded to fp16 once (reference sums fp32 products)
+    assert rel(stats, _moments(ref, 32).float()) < 2e-3
+
+
 def test_mrf_combine():
     torch.manual_seed(32)
     slope = 0.1
