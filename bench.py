@@ -209,7 +209,7 @@ def main():
         if stages == "all":
             out_h.copy_(r["int16"][:, :CLIP_SAMPLES], non_blocking=True)
             if world > 1:  # NCCL is used only to gather the waveforms for output (north_star)
-                gather_waveforms(r["int16"][:, :CLIP_SAMPLES], B * world)
+                gather_waveforms(r["int16"][:, :CLIP_SAMPLES], B * world, sizes=[B] * world)
         else:
             lat_h.copy_(r["latent"], non_blocking=True)
     for _ in range(2):

@@ -44,14 +44,18 @@ def global_minmax(minmax):
     return minmax
 
 
-def gather_waveforms(local, n_global=None):
-    """All-gathers int16 [B_local, T] shards (possibly unequal B_local) into [n_global, T] on every rank."""
+def gather_waveforms(local, n_global=None, sizes=None):
+    """All-gathers int16 [B_local, T] shards (possibly unequal B_local) into [n_global, T] on every rank.
+    `sizes` (rows per rank) skips the size exchange and its host synchronisation when the split is known, e.g.
+    [shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0] for r in range(world)]."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return local
     world = dist.get_world_size()
-    sizes = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device))
-    sizes = [int(s.item()) for s in sizes]
+    if sizes is None:
+        sizes = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device))
+        sizes = [int(s.item()) for s in sizes]
+    assert len(sizes) == world and sizes[dist.get_rank()] == local.shape[0]
     m = max(sizes)
     # neither NCCL nor gloo transports int16: ship the raw bytes
     row_bytes = local.element_size()
