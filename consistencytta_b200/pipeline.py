@@ -237,8 +237,11 @@ class ConsistencyTTA(nn.Module):
 
     @torch.no_grad()
     def generate_from_embeddings(self, prompt_embeds, prompt_mask=None, cfg_scale_input=3.0, cfg_scale_post=1.0,
-                                 num_steps=1, noise=None, uncond_embeds=None, uncond_mask=None, return_all=False):
-        """The hot path of forward() for given text-encoder outputs.  prompt_embeds [B, L, 1024]."""
+                                 num_steps=1, noise=None, uncond_embeds=None, uncond_mask=None, return_all=False,
+                                 step_noises=None):
+        """The hot path of forward() for given text-encoder outputs.  prompt_embeds [B, L, 1024].
+        `step_noises` (optional list of [B,8,256,16] tensors) replaces the `torch.randn_like` draws of the multi-step
+        re-noising (consistencytta.py:193) so that a run can be reproduced against the oracle."""
         self.check_eval_mode()
         dev = self.unet.device
         b = prompt_embeds.shape[0]
@@ -262,10 +265,11 @@ class ConsistencyTTA(nn.Module):
         out = self.engine.run(noise, enc, mask, cfg_scale_input, cfg_scale_post, t0, sigma, stages="unet")
         zhat = out["latent"].clone()
         self.scheduler.set_timesteps(num_steps)
-        for t in self.scheduler.timesteps[1::2]:
+        for i, t in enumerate(self.scheduler.timesteps[1::2]):
             sig_t = float(self.scheduler.sigma_for_timestep(t))
             # add_noise then scale_model_input: (zhat + n * sig_t) / sqrt(sig_t^2 + 1) == noise' * sig' form of run()
-            zn = self.scheduler.add_noise(zhat, torch.randn_like(zhat), t)
+            n_i = step_noises[i].to(zhat) if step_noises is not None else torch.randn_like(zhat)
+            zn = self.scheduler.add_noise(zhat, n_i, t)
             out = self.engine.run(zn / sig_t if sig_t > 0 else zn, enc, mask, cfg_scale_input, cfg_scale_post,
                                   float(t), sig_t if sig_t > 0 else 1.0, stages="unet")
             zhat = out["latent"].clone()

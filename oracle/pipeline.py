@@ -39,3 +39,32 @@ def generate(unet_sd, vae_sd, scale_factor, noise, enc, enc_mask, guidance, guid
     mel = vae.decode_first_stage(vae_sd, out.float(), scale_factor)
     wav = hifigan.decode_to_waveform(vae_sd, mel, return_float=True)
     return out, mel, wav
+
+
+def heun_schedule(num_inference_steps, num_train_timesteps=1000):
+    """(timesteps, sigmas) after set_timesteps(n), interleaved as the second-order scheduler stores them
+    (scheduling_heun_discrete.py:174-227): timesteps [t0, t1, t1, t2, t2, ...], sigmas [s0, s1, s1, ..., 0]."""
+    sig = heun_sigmas(num_train_timesteps)
+    ts = np.linspace(0, num_train_timesteps - 1, num_inference_steps, dtype=float)[::-1].copy()
+    sg = np.interp(ts, np.arange(0, len(sig)), sig).astype(np.float32)
+    sg = np.concatenate([sg, [0.0]]).astype(np.float32)
+    timesteps = np.concatenate([ts[:1], np.repeat(ts[1:], 2)])
+    sigmas = np.concatenate([sg[:1], np.repeat(sg[1:-1], 2), sg[-1:]])
+    return timesteps, sigmas
+
+
+def generate_latent_multistep(unet_sd, noise, step_noises, enc, enc_mask, guidance, num_steps):
+    """Multi-step consistency sampling, easy_inference/consistencytta.py:186-197: query at timesteps[0] of the 18-step
+    schedule, then for every t in set_timesteps(num_steps).timesteps[1::2]: re-noise zhat_0 with `add_noise`
+    (z + n * sigma_t, scheduling_heun_discrete.py:364-385), `scale_model_input`, query again."""
+    t0, sigma = heun_first_step()
+    z_in = noise * sigma / ((sigma ** 2 + 1) ** 0.5)
+    zhat = unet.unet_forward(unet_sd, z_in, torch.tensor(t0, dtype=torch.float64), guidance, enc, enc_mask)
+    timesteps, sigmas = heun_schedule(num_steps)
+    for i, t in enumerate(timesteps[1::2]):
+        idx = int(np.argmax(timesteps == t))   # index_for_timestep: first match
+        sig_t = float(sigmas[idx])
+        zn = zhat + step_noises[i] * sig_t
+        zn = zn / ((sig_t ** 2 + 1) ** 0.5)
+        zhat = unet.unet_forward(unet_sd, zn, torch.tensor(float(t), dtype=torch.float64), guidance, enc, enc_mask)
+    return zhat

@@ -112,3 +112,42 @@ def test_modules_refuse_cpu():
     assert len(u.state_dict()) == 691
     with pytest.raises(RuntimeError):
         u(torch.zeros(1, 8, 256, 16), 999.0, guidance=4.0, encoder_hidden_states=torch.zeros(1, 4, 1024))
+
+
+def test_oracle_heun_schedule_matches_scheduler():
+    """oracle.heun_schedule (used by the multi-step oracle) against the product's HeunDiscreteScheduler mirror."""
+    from consistencytta_b200 import HeunDiscreteScheduler
+    from oracle import pipeline as op
+    s = HeunDiscreteScheduler.from_pretrained()
+    for n in (2, 4, 18):
+        s.set_timesteps(n)
+        ts, sg = op.heun_schedule(n)
+        assert np.allclose(s.timesteps.numpy(), ts) and np.allclose(s.sigmas.numpy(), sg)
+        for t in s.timesteps[1::2]:
+            idx = int(np.argmax(ts == float(t)))
+            assert abs(float(s.sigma_for_timestep(t)) - float(sg[idx])) < 1e-7
+
+
+def test_audiolcm_load_pretrained_key_remap():
+    """models/audio_consistency_model.py:160-204: consistency_ema_* -> student_target_* (and student_ema_* unless a
+    consistency_slow_ema_* key exists); trainable student, teacher, VAE and loss tensors are not used at inference."""
+    from consistencytta_b200 import AudioLCM
+    m = AudioLCM()
+    w = m.student_target_unet.conv_in.weight
+    b = m.student_target_unet.conv_in.bias
+    ckpt = {
+        "consistency_ema_unet.conv_in.weight": torch.full_like(w, 1.0),
+        "consistency_slow_ema_unet.conv_in.weight": torch.full_like(w, 2.0),
+        "consistency_ema_unet.conv_in.bias": torch.full_like(b, 3.0),
+        "consistency_unet.conv_in.weight": torch.full_like(w, 9.0),
+        "diffusion_unet.conv_in.weight": torch.full_like(w, 9.0),
+        "vae.decoder.conv_in.weight": torch.zeros(3),
+        "loss.window": torch.zeros(3),
+    }
+    info = m.load_pretrained(ckpt)
+    assert not info.unexpected_keys
+    assert (m.student_target_unet.conv_in.weight == 1.0).all()
+    assert (m.student_ema_unet.conv_in.weight == 2.0).all()          # slow EMA wins
+    assert (m.student_target_unet.conv_in.bias == 3.0).all()
+    assert (m.student_ema_unet.conv_in.bias == 3.0).all()            # no slow EMA -> copy of the EMA weights
+    m.check_eval_mode()
