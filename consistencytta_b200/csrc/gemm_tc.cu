@@ -1216,6 +1216,12 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
         block_n = bn;
       }
     }
+    // small-M problems (the UNet's 32x2 / 64x4 levels): a 128 x 256 tiling leaves most SMs idle; halve the tile width
+    // while the tile count still fits one wave
+    const long long m_tiles = (static_cast<long long>(d->n_img) * d->rows_per_img + kBlockM - 1) / kBlockM;
+    while (block_n >= 128 && block_n % 64 == 0 && d->n % (block_n / 2) == 0 &&
+           2 * m_tiles * ((d->n + block_n - 1) / block_n) <= sm_count() && getenv("CTTA_NO_NARROW_TILES") == nullptr)
+      block_n /= 2;
   }
   p.block_n = block_n;
   p.n_tiles_n = (d->n + block_n - 1) / block_n;
