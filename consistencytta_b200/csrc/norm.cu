@@ -43,6 +43,7 @@ __device__ __forceinline__ void store4(void* base, int dtype, long long elem_off
 // grid (slabs, n_img); block (32, 8): x = 4-channel vector column (coalesced), y = row within the slab.
 // Each thread owns fixed vector columns, so its partial sums belong to one group per column.
 constexpr int kGnMaxGroups = 64;
+constexpr int kGnMaxChannels = 2048;   // widest normalised tensor: torch.cat([x, skip]) of the UNet's first up block
 
 __global__ void __launch_bounds__(256) gn_moments_kernel(const void* __restrict__ x, int x_dtype, int c, int ld,
                                                          const void* __restrict__ x2, int c2, int ld2, int hw,
@@ -161,8 +162,11 @@ __global__ void __launch_bounds__(256, kIn16 ? 3 : 5) gn_apply_kernel(const void
                                                        int groups, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, int act, int up, void* __restrict__ y, int y_dtype,
-                                                       int y_ld, void* __restrict__ raw, int raw_ld) {
+                                                       int y_ld, void* __restrict__ raw, int raw_ld, int nshift) {
+  // per-channel affine of this image: y = x * s_a[c] + s_b[c] with s_a = rstd[g] gamma[c], s_b = beta[c] - mean[g] s_a
+  // (built once per block: one FMA per element in the loop, no per-item group lookup / gamma / beta loads)
   __shared__ float s_mean[kGnMaxGroups], s_rstd[kGnMaxGroups];
+  __shared__ __align__(16) float s_a[kGnMaxChannels], s_b[kGnMaxChannels];
   const int n = blockIdx.y;
   const int ctot = c + c2;
   const int hw = h * w;
@@ -177,6 +181,15 @@ __global__ void __launch_bounds__(256, kIn16 ? 3 : 5) gn_apply_kernel(const void
     s_rstd[threadIdx.x] = rsqrtf(var + eps);
   }
   __syncthreads();
+  if (stats) {
+    for (int ch = threadIdx.x; ch < ctot; ch += blockDim.x) {
+      const int g = ch / cpg;
+      const float a = s_rstd[g] * gamma[ch];
+      s_a[ch] = a;
+      s_b[ch] = beta[ch] - s_mean[g] * a;
+    }
+    __syncthreads();
+  }
   const unsigned nvec = static_cast<unsigned>(ctot) >> 3;
   const unsigned total = static_cast<unsigned>(hw) * nvec;  // < 2^31: checked on the host
   const unsigned step = gridDim.x * blockDim.x;
@@ -189,7 +202,7 @@ __global__ void __launch_bounds__(256, kIn16 ? 3 : 5) gn_apply_kernel(const void
 #pragma unroll
     for (int k = 0; k < kGnItems; ++k) {
       const unsigned idx = base + k * step;
-      const unsigned pix_k = idx / nvec;
+      const unsigned pix_k = nshift >= 0 ? idx >> nshift : idx / nvec;   // nvec is a power of two except for some concats
       const unsigned ch_k = (idx - pix_k * nvec) << 3;
       if (idx < total) {
         const bool second = ch_k >= static_cast<unsigned>(c);
@@ -204,27 +217,22 @@ __global__ void __launch_bounds__(256, kIn16 ? 3 : 5) gn_apply_kernel(const void
     for (int k = 0; k < kGnItems; ++k) {
       const unsigned idx = base + k * step;   // (recomputed rather than kept: registers are what limits occupancy)
       if (idx >= total) continue;
-      const unsigned pix_k = idx / nvec;
+      const unsigned pix_k = nshift >= 0 ? idx >> nshift : idx / nvec;
       const unsigned ch_k = (idx - pix_k * nvec) << 3;
       Vec8& fk = f[kIn16 ? 0 : k];
       if (kIn16) fk = unpack8(r16[k], x_dtype);
       if (raw) store8(raw, y_dtype, (img_row0 + pix_k) * raw_ld + ch_k, fk);
       if (stats) {
-        const int g = ch_k / cpg;  // 8 | cpg is not required: 4 | cpg, so the vector may straddle two groups
-        const int g2 = (ch_k + 4) / cpg;
-        const float m0 = s_mean[g], r0 = s_rstd[g], m1 = s_mean[g2], r1 = s_rstd[g2];
-        const float4 ga0 = __ldg(reinterpret_cast<const float4*>(gamma + ch_k));
-        const float4 ga1 = __ldg(reinterpret_cast<const float4*>(gamma + ch_k) + 1);
-        const float4 be0 = __ldg(reinterpret_cast<const float4*>(beta + ch_k));
-        const float4 be1 = __ldg(reinterpret_cast<const float4*>(beta + ch_k) + 1);
-        fk.v[0] = (fk.v[0] - m0) * r0 * ga0.x + be0.x;
-        fk.v[1] = (fk.v[1] - m0) * r0 * ga0.y + be0.y;
-        fk.v[2] = (fk.v[2] - m0) * r0 * ga0.z + be0.z;
-        fk.v[3] = (fk.v[3] - m0) * r0 * ga0.w + be0.w;
-        fk.v[4] = (fk.v[4] - m1) * r1 * ga1.x + be1.x;
-        fk.v[5] = (fk.v[5] - m1) * r1 * ga1.y + be1.y;
-        fk.v[6] = (fk.v[6] - m1) * r1 * ga1.z + be1.z;
-        fk.v[7] = (fk.v[7] - m1) * r1 * ga1.w + be1.w;
+        const float4 a0 = *reinterpret_cast<const float4*>(s_a + ch_k), a1 = *reinterpret_cast<const float4*>(s_a + ch_k + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(s_b + ch_k), b1 = *reinterpret_cast<const float4*>(s_b + ch_k + 4);
+        fk.v[0] = fmaf(fk.v[0], a0.x, b0.x);
+        fk.v[1] = fmaf(fk.v[1], a0.y, b0.y);
+        fk.v[2] = fmaf(fk.v[2], a0.z, b0.z);
+        fk.v[3] = fmaf(fk.v[3], a0.w, b0.w);
+        fk.v[4] = fmaf(fk.v[4], a1.x, b1.x);
+        fk.v[5] = fmaf(fk.v[5], a1.y, b1.y);
+        fk.v[6] = fmaf(fk.v[6], a1.z, b1.z);
+        fk.v[7] = fmaf(fk.v[7], a1.w, b1.w);
       }
       if (act == CTTA_ACT_SILU) {
         if (kIn16) {
@@ -390,6 +398,7 @@ extern "C" int ctta_groupnorm_apply(const void* x, int32_t x_dtype, int32_t c, i
   CTTA_REQUIRE(al16(x) && (!x2 || al16(x2)) && al16(y) && (!raw_out || al16(raw_out)),
                "groupnorm_apply: tensors must be 16-byte aligned");
   if (stats) {
+    CTTA_REQUIRE(c + c2 <= kGnMaxChannels, "groupnorm_apply: at most %d channels", kGnMaxChannels);
     CTTA_REQUIRE(gamma && beta && groups > 0 && groups <= kGnMaxGroups && (c + c2) % groups == 0 &&
                      ((c + c2) / groups) % 4 == 0 && al16(gamma) && al16(beta),
                  "groupnorm_apply: bad group configuration");
@@ -398,6 +407,12 @@ extern "C" int ctta_groupnorm_apply(const void* x, int32_t x_dtype, int32_t c, i
   CTTA_REQUIRE(act == CTTA_ACT_NONE || act == CTTA_ACT_SILU, "groupnorm_apply: act must be NONE or SILU");
   const long long total = static_cast<long long>(h) * w * ((c + c2) / 8);
   const int items = x_dtype == CTTA_F32 ? 2 : 8;
+  const int nvec_h = (c + c2) / 8;
+  int nshift = -1;
+  if ((nvec_h & (nvec_h - 1)) == 0) {
+    nshift = 0;
+    while ((1 << nshift) < nvec_h) ++nshift;
+  }
   long long blocks = (total + 256 * items - 1) / (256 * items);
   const long long cap = (static_cast<long long>(sm_count()) * 32 + n_img - 1) / n_img;
   if (blocks > cap) blocks = cap;
@@ -405,10 +420,10 @@ extern "C" int ctta_groupnorm_apply(const void* x, int32_t x_dtype, int32_t c, i
   dim3 grid(static_cast<unsigned>(blocks), n_img);
   if (items == 2)
     gn_apply_kernel<2, false><<<grid, 256, 0, stream>>>(x, x_dtype, c, ld, x2, c2, ld2, h, w, groups, stats, gamma, beta,
-                                                 eps, act, upsample2x, y, y_dtype, y_ld, raw_out, raw_ld);
+                                                 eps, act, upsample2x, y, y_dtype, y_ld, raw_out, raw_ld, nshift);
   else
     gn_apply_kernel<8, true><<<grid, 256, 0, stream>>>(x, x_dtype, c, ld, x2, c2, ld2, h, w, groups, stats, gamma, beta,
-                                                 eps, act, upsample2x, y, y_dtype, y_ld, raw_out, raw_ld);
+                                                 eps, act, upsample2x, y, y_dtype, y_ld, raw_out, raw_ld, nshift);
   CTTA_LAUNCH_CHECK();
   return 0;
 }
