@@ -12,6 +12,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Pins a value in a register: ptxas may not re-derive it at each use (it does so for shared-window addresses, with an
+// S2UR SR_CgaCtaId per use, which costs a single-thread issue loop ~30 cycles of uniform-datapath latency each time).
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
 // One lane of a CONVERGED warp.  Unlike `lane == 0`, ptxas knows exactly one thread is active behind this predicate,
 // so warp-uniform instructions (UTCHMMA, UTMALDG, UTMASTG, UTCBAR) are issued straight instead of inside an
 // ELECT / BRA.U.ANY serialisation loop (about 12 extra SASS instructions per tcgen05.mma otherwise).

@@ -16,6 +16,7 @@
 //
 // Reference call sites replaced: see ctta_gemm in include/ctta.h.
 #include <cuda.h>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -117,8 +118,12 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile) {
   TileCoord tc;
-  const int m_tile = tile / p.n_tiles_n;
-  tc.n0 = (tile - m_tile * p.n_tiles_n) * p.block_n;
+  int m_tile = tile;
+  tc.n0 = 0;
+  if (p.n_tiles_n != 1) {   // (one N tile: no division on the per-tile path of the narrow convolutions)
+    m_tile = tile / p.n_tiles_n;
+    tc.n0 = (tile - m_tile * p.n_tiles_n) * p.block_n;
+  }
   if (p.a_mode == CTTA_A_ROWS) {
     tc.c1 = m_tile * kBlockM * p.sub_tiles;
     tc.c2 = 0;
@@ -352,6 +357,46 @@ __device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
   return r;
 }
 
+// Packed fp32 pairs (FADD2 / FMUL2 on sm_100): IEEE round-to-nearest like the scalar forms, half the issue slots.  The
+// TMA-staged epilogue is issue-bound on the narrow convolutions (8 warps x ~500 instructions per 32 x 32 chunk).
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  uint64_t a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+__device__ __forceinline__ void mul2s(float& o0, float& o1, float a0, float a1, float s) {
+  uint64_t a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(s));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(a));
+}
+// LeakyReLU of a pair: max(v, slope * v) for slope in [0, 1] (min for slope > 1) == v > 0 ? v : slope * v
+__device__ __forceinline__ void lrelu2(float& v0, float& v1, float slope) {
+  float m0, m1;
+  mul2s(m0, m1, v0, v1, slope);
+  if (slope <= 1.f) {
+    v0 = fmaxf(v0, m0);
+    v1 = fmaxf(v1, m1);
+  } else {
+    v0 = fminf(v0, m0);
+    v1 = fminf(v1, m1);
+  }
+}
+// in-place activation of an even-length register array
+template <int N>
+__device__ __forceinline__ void act_apply_n(float* v, int act, float slope) {
+  if (act == CTTA_ACT_LRELU) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) lrelu2(v[i], v[i + 1], slope);
+  } else if (act != CTTA_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = act_apply(v[i], act, slope);
+  }
+}
+
 // GroupNorm moments of one 32-column chunk: v[32] = this thread's row, NG = groups inside the chunk (32 / cpg, or 1
 // when a group spans the whole chunk).  Rows are summed across the warp with a halving butterfly (NG * 2 values ->
 // one value per lane after log2(2 NG) exchange steps), then one red.global per (group, moment).
@@ -421,44 +466,46 @@ __device__ __forceinline__ void umma_halo_taps(const GemmKParams& p, uint32_t d_
   }
 }
 
+struct GemmBars {
+  uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2], ring_full[kMaxRing], ring_empty[kMaxRing],
+      weights[1], a_full[kMaxAStages], a_empty[kMaxAStages];
+};
+#define BAR(field, idx) (bar_base + static_cast<uint32_t>(offsetof(GemmBars, field)) + 8u * static_cast<uint32_t>(idx))
+
 template <class Cfg>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
                const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[kMaxStages];
-  __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
-  __shared__ __align__(8) uint64_t bar_tmem_full[2];
-  __shared__ __align__(8) uint64_t bar_tmem_empty[2];
-  __shared__ __align__(8) uint64_t bar_ring_full[kMaxRing];
-  __shared__ __align__(8) uint64_t bar_ring_empty[kMaxRing];
-  __shared__ __align__(8) uint64_t bar_weights;
-  __shared__ __align__(8) uint64_t bar_a_full[kMaxAStages];
-  __shared__ __align__(8) uint64_t bar_a_empty[kMaxAStages];
+  // every mbarrier lives in ONE static block and is addressed as (pinned base register + constant offset): taking the
+  // shared-window address of each array separately makes ptxas re-derive it with an S2UR SR_CgaCtaId (~30 cycles of
+  // uniform-datapath latency) at every use inside the single-thread issue loops
+  __shared__ __align__(8) GemmBars bars_s;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-B alignment
+  const uint32_t tiles_base = pin_u32((smem_u32(smem_raw) + 1023u) & ~1023u);  // SWIZZLE_128B needs 1024-B alignment
+  const uint32_t bar_base = pin_u32(smem_u32(&bars_s));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(BAR(full, s), 1);
+      mbar_init(BAR(empty, s), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bar_tmem_full[s]), 1);
-      mbar_init(smem_u32(&bar_tmem_empty[s]), p.epi_tma ? 4 * p.epi_groups : 4);  // one arrive per epilogue warp
+      mbar_init(BAR(tmem_full, s), 1);
+      mbar_init(BAR(tmem_empty, s), p.epi_tma ? 4 * p.epi_groups : 4);  // one arrive per epilogue warp
     }
     for (int s = 0; s < kMaxRing; ++s) {
-      mbar_init(smem_u32(&bar_ring_full[s]), 1);
-      mbar_init(smem_u32(&bar_ring_empty[s]), 4);
+      mbar_init(BAR(ring_full, s), 1);
+      mbar_init(BAR(ring_empty, s), 4);
     }
-    mbar_init(smem_u32(&bar_weights), 1);
+    mbar_init(BAR(weights, 0), 1);
     for (int s = 0; s < kMaxAStages; ++s) {
-      mbar_init(smem_u32(&bar_a_full[s]), 1);
-      mbar_init(smem_u32(&bar_a_empty[s]), 1);
+      mbar_init(BAR(a_full, s), 1);
+      mbar_init(BAR(a_empty, s), 1);
     }
     mbar_fence_init();
     tma_prefetch_desc(&tmap_a);
@@ -495,8 +542,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const TileCoord tc = decode_tile(p, tile);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           for (int j = 0; j < p.ntaps; ++j) {   // taps are stored group by group
-            mbar_wait(smem_u32(&bar_empty[w_stage]), w_phase ^ 1u);
-            const uint32_t wfull = smem_u32(&bar_full[w_stage]);
+            mbar_wait(BAR(empty, w_stage), w_phase ^ 1u);
+            const uint32_t wfull = BAR(full, w_stage);
             mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(p.w_stage_bytes));
             tma_load_2d(w_base + w_stage * p.w_stage_bytes, &tmap_b, wfull, (p.tap_id[j] * p.k_chunks + kc) * kBlockK,
                         tc.n0);
@@ -509,7 +556,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     } else if (leader && p.halo) {
       // resident weights: one {64 x block_n} box per tap, loaded once per CTA
-      const uint32_t wbar = smem_u32(&bar_weights);
+      const uint32_t wbar = BAR(weights, 0);
       mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(p.w_bytes));
       for (int j = 0; j < p.ntaps; ++j)
         tma_load_2d(tiles_base + static_cast<uint32_t>(j * p.block_n * 128), &tmap_b, wbar, j * kBlockK, 0);
@@ -519,8 +566,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         for (int sub = 0; sub < p.sub_tiles; ++sub) {
-          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-          const uint32_t full = smem_u32(&bar_full[stage]);
+          mbar_wait(BAR(empty, stage), phase ^ 1u);
+          const uint32_t full = BAR(full, stage);
           mbar_arrive_expect_tx(full, tx_bytes);
           tma_load_3d(stages_base + static_cast<uint32_t>(stage * p.stage_bytes), &tmap_a, full, 0,
                       tc.c1 + sub * kBlockM + p.halo_min_shift, tc.c2);
@@ -542,8 +589,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int j = 0; j < p.ntaps; ++j) {
             const int d0 = p.tap_d0[j], d1 = p.tap_d1[j];
             for (int kc = 0; kc < p.k_chunks; ++kc, ++kb) {
-              mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-              const uint32_t full = smem_u32(&bar_full[stage]);
+              mbar_wait(BAR(empty, stage), phase ^ 1u);
+              const uint32_t full = BAR(full, stage);
               mbar_arrive_expect_tx(full, tx_bytes);
               const uint32_t a_dst = stages_base + static_cast<uint32_t>(stage * p.stage_bytes);
               const uint32_t b_dst = a_dst + kATileBytes;
@@ -577,18 +624,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = p.acc_single ? 0 : (it & 1);
         const uint32_t acc_phase = p.acc_single ? (it & 1) : ((it >> 1) & 1);
-        mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
+        mbar_wait(BAR(tmem_empty, acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
         uint32_t started = 0;   // 0 until the first MMA of every sub-tile has been issued
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           const int nkk = (kc == p.k_chunks - 1) ? p.kk_last : kBlockK / 16;
           for (int g = 0; g < p.n_groups; ++g) {
-            mbar_wait(smem_u32(&bar_a_full[a_stage]), a_phase);
+            mbar_wait(BAR(a_full, a_stage), a_phase);
             const uint32_t a_base = tiles_base + static_cast<uint32_t>(a_stage * p.a_stage_bytes);
             const int j1 = p.grp_first[g] + p.grp_count[g];
             for (int j = p.grp_first[g]; j < j1; ++j) {
-              mbar_wait(smem_u32(&bar_full[w_stage]), w_phase);
+              mbar_wait(BAR(full, w_stage), w_phase);
               tc_fence_after();
               const uint32_t b_lo = umma_desc_lo(w_base + static_cast<uint32_t>(w_stage * p.w_stage_bytes));
               const uint32_t a_lo = umma_desc_lo(a_base) + static_cast<uint32_t>(p.tap_rows[j]) * 8u;
@@ -600,33 +647,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   umma_chunk_n(nkk, d_tmem + sub * p.block_n, a_lo + sub * (kBlockM * 8), b_lo, idesc, started);
               }
               started = 1;
-              umma_commit(smem_u32(&bar_empty[w_stage]));
+              umma_commit(BAR(empty, w_stage));
               if (++w_stage == p.n_stages) {
                 w_stage = 0;
                 w_phase ^= 1u;
               }
             }
-            umma_commit(smem_u32(&bar_a_empty[a_stage]));
+            umma_commit(BAR(a_empty, a_stage));
             if (++a_stage == p.n_a_stages) {
               a_stage = 0;
               a_phase ^= 1u;
             }
           }
         }
-        umma_commit(smem_u32(&bar_tmem_full[acc]));
+        umma_commit(BAR(tmem_full, acc));
       }
     } else if (leader && p.halo) {
       const uint32_t idesc = umma_idesc(kBlockM, p.block_n, p.is_bf16);
-      mbar_wait(smem_u32(&bar_weights), 0);
+      mbar_wait(BAR(weights, 0), 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = p.acc_single ? 0 : (it & 1);
         const uint32_t acc_phase = p.acc_single ? (it & 1) : ((it >> 1) & 1);
-        mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
+        mbar_wait(BAR(tmem_empty, acc), acc_phase ^ 1u);
         for (int sub = 0; sub < p.sub_tiles; ++sub) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          mbar_wait(BAR(full, stage), phase);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride + sub * p.block_n);
           const uint32_t a_base = stages_base + static_cast<uint32_t>(stage * p.stage_bytes);
@@ -642,13 +689,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               default: umma_halo_taps<4>(p, d_tmem, a_lo0, b_lo0, b_step, idesc); break;
             }
           }
-          umma_commit(smem_u32(&bar_empty[stage]));
+          umma_commit(BAR(empty, stage));
           if (++stage == p.n_stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(smem_u32(&bar_tmem_full[acc]));
+        umma_commit(BAR(tmem_full, acc));
       }
     } else if (leader) {
       const uint32_t idesc = umma_idesc(kBlockM, p.block_n, p.is_bf16);
@@ -658,13 +705,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = p.acc_single ? 0 : (it & 1);
         const uint32_t acc_phase = p.acc_single ? (it & 1) : ((it >> 1) & 1);
-        mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
+        mbar_wait(BAR(tmem_empty, acc), acc_phase ^ 1u);
         tc_fence_after();
         for (int sub = 0; sub < p.sub_tiles; ++sub) {
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride + sub * p.block_n);
         int kc = 0;
         for (int kb = 0; kb < k_iters; ++kb) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          mbar_wait(BAR(full, stage), phase);
           tc_fence_after();
           const uint32_t a_lo = umma_desc_lo(stages_base + static_cast<uint32_t>(stage * p.stage_bytes));
           const uint32_t b_lo = a_lo + (kATileBytes >> 4);
@@ -672,7 +719,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             umma_chunk<4>(d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
           else
             umma_chunk_n(p.kk_last, d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);  // skip all-zero K slices
-          umma_commit(smem_u32(&bar_empty[stage]));  // frees the smem stage once these MMAs retire
+          umma_commit(BAR(empty, stage));  // frees the smem stage once these MMAs retire
           if (++kc == p.k_chunks) kc = 0;
           if (++stage == p.n_stages) {
             stage = 0;
@@ -680,7 +727,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         }
-        umma_commit(smem_u32(&bar_tmem_full[acc]));  // accumulator complete -> epilogue
+        umma_commit(BAR(tmem_full, acc));  // accumulator complete -> epilogue
       }
     }
   } else if (warp == kALoaderWarp) {
@@ -693,8 +740,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const TileCoord tc = decode_tile(p, tile);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           for (int g = 0; g < p.n_groups; ++g) {
-            mbar_wait(smem_u32(&bar_a_empty[a_stage]), a_phase ^ 1u);
-            const uint32_t afull = smem_u32(&bar_a_full[a_stage]);
+            mbar_wait(BAR(a_empty, a_stage), a_phase ^ 1u);
+            const uint32_t afull = BAR(a_full, a_stage);
             mbar_arrive_expect_tx(afull, a_box_bytes * p.a_loads);
             const uint32_t a_dst = tiles_base + static_cast<uint32_t>(a_stage * p.a_stage_bytes);
             if (p.a_mode == CTTA_A_CONV1D) {
@@ -738,8 +785,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int col = tc.n0 + ch * kChunkCols;
           const int srow0 = row0 + sub * kBlockM;
           for (int k = 0; k < p.ring_per_chunk; ++k) {
-            mbar_wait(smem_u32(&bar_ring_empty[slot]), phase ^ 1u);
-            const uint32_t full = smem_u32(&bar_ring_full[slot]);
+            mbar_wait(BAR(ring_empty, slot), phase ^ 1u);
+            const uint32_t full = BAR(ring_full, slot);
             if (k < p.ring_in) {
               mbar_arrive_expect_tx(full, static_cast<uint32_t>(p.ring_slot_bytes));
               // the fp32 residual tile: one {32 cols x 32 rows} box per epilogue warp (the box shape the stores use)
@@ -797,7 +844,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const long long ra_row =
           p.rowadd ? (static_cast<long long>(img) * p.rows_per_img + r) / p.rowadd_rows : 0;
 
-      mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
+      mbar_wait(BAR(tmem_full, acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
@@ -810,7 +857,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+          if (lane == 0) mbar_arrive(BAR(tmem_empty, acc));
         }
         if (valid) {
           const int ncols = wide ? 32 : 16;
@@ -863,6 +910,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int wrow_in_img = wrow % p.out_rows_tile_img;
     const int wimg = wrow / p.out_rows_tile_img;
     uint32_t my_ctr = 0;    // chunks processed by this warp (staging buffer parity)
+    const bool bias_once = p.n_tiles_n == 1;
+    // ring position of global chunk (it * tot_chunks): slot index and phase advance incrementally (no 64-bit div / mod
+    // per chunk); tile_adv_q / tile_adv_r = (tot_chunks * ring_per_chunk) div / mod ring_slots
+    int tile_slot = 0;
+    uint32_t tile_phase = 0;
+    int tile_adv_q = 0, tile_adv_r = 0;
+    if (ring_per_chunk > 0) {
+      tile_adv_q = (tot_chunks * ring_per_chunk) / p.ring_slots;
+      tile_adv_r = (tot_chunks * ring_per_chunk) - tile_adv_q * p.ring_slots;
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = p.acc_single ? 0 : (it & 1);
@@ -876,6 +933,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       } else {
         row0 = tc.c2 * p.W + tc.c1; img0 = tc.c3;
       }
+      // ring position of this warp's first chunk (cc = grp) and of the next tile
+      int c_slot = tile_slot + grp * ring_per_chunk;
+      uint32_t c_phase = tile_phase;
+      while (ring_per_chunk > 0 && c_slot >= p.ring_slots) { c_slot -= p.ring_slots; c_phase ^= 1u; }
+      tile_slot += tile_adv_r;
+      tile_phase ^= static_cast<uint32_t>(tile_adv_q & 1);
+      if (ring_per_chunk > 0 && tile_slot >= p.ring_slots) { tile_slot -= p.ring_slots; tile_phase ^= 1u; }
       // this warp's 32 rows: coordinates of the store box (of sub-tile 0)
       const int st_row0 = row0 + wrow_in_img - p.row_coord_shift;
       const int st_img = img0 + wimg;
@@ -886,23 +950,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         ra_gr0 = static_cast<long long>(img) * p.rows_per_img + r_in_img;
         ra_gmax = static_cast<long long>(p.n_img) * p.rows_per_img - 1;  // rows past the end are clipped by the TMA store
       }
-      // bias of this tile -> shared memory (double buffered by tile parity)
-      float* bs = bias_s + (it & 1) * 256;
-      for (int i = et; i < p.block_n; i += ngrp * 128) {
-        const int c = tc.n0 + i;
-        bs[i] = (p.bias != nullptr && c < p.N) ? p.bias[c] : 0.f;
+      // bias of this tile -> shared memory (double buffered by tile parity); with a single N tile it never changes
+      float* bs = bias_s + (bias_once ? 0 : (it & 1) * 256);
+      if (!bias_once || it == 0) {
+        for (int i = et; i < p.block_n; i += ngrp * 128) {
+          const int c = tc.n0 + i;
+          bs[i] = (p.bias != nullptr && c < p.N) ? p.bias[c] : 0.f;
+        }
+        named_barrier_sync(1, ngrp * 128);
       }
-      named_barrier_sync(1, ngrp * 128);
 
-      mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
+      mbar_wait(BAR(tmem_full, acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
-      const long long chunk_base = static_cast<long long>(it) * tot_chunks;
       const int last_cc = ((tot_chunks - 1 - grp) / ngrp) * ngrp + grp;  // last chunk of this group
       if (grp >= tot_chunks) {
         // nothing to read from this accumulator stage
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+        if (lane == 0) mbar_arrive(BAR(tmem_empty, acc));
       }
       int sub = 0, ch = grp;
       while (ch >= n_chunks) { ch -= n_chunks; ++sub; }
@@ -928,21 +993,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (cc == last_cc) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+          if (lane == 0) mbar_arrive(BAR(tmem_empty, acc));
         }
         float v[32];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 b4 = *reinterpret_cast<const float4*>(bs + c0 + 4 * g);
-          v[4 * g + 0] = __uint_as_float(u[4 * g + 0]) + b4.x;
-          v[4 * g + 1] = __uint_as_float(u[4 * g + 1]) + b4.y;
-          v[4 * g + 2] = __uint_as_float(u[4 * g + 2]) + b4.z;
-          v[4 * g + 3] = __uint_as_float(u[4 * g + 3]) + b4.w;
+          v[4 * g + 0] = __uint_as_float(u[4 * g + 0]);
+          v[4 * g + 1] = __uint_as_float(u[4 * g + 1]);
+          v[4 * g + 2] = __uint_as_float(u[4 * g + 2]);
+          v[4 * g + 3] = __uint_as_float(u[4 * g + 3]);
+          add2(v[4 * g + 0], v[4 * g + 1], b4.x, b4.y);
+          add2(v[4 * g + 2], v[4 * g + 3], b4.z, b4.w);
         }
         if (has_rowadd) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            v[4 * g + 0] += ra[g].x; v[4 * g + 1] += ra[g].y; v[4 * g + 2] += ra[g].z; v[4 * g + 3] += ra[g].w;
+            add2(v[4 * g + 0], v[4 * g + 1], ra[g].x, ra[g].y);
+            add2(v[4 * g + 2], v[4 * g + 3], ra[g].z, ra[g].w);
           }
         }
         const uint32_t st16 = st16_base + (my_ctr & 1) * kStage16Bytes;
@@ -967,20 +1035,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           __syncwarp();
         } else {
-          if (act != CTTA_ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], act, p.act_slope);
-          }
+          act_apply_n<32>(v, act, p.act_slope);
           // ---- fp32 inputs from the ring (residual, previous out)
           uint32_t slot_addr = 0;
           int first_slot = -1;
           if (ring_per_chunk > 0) {
-            const long long s0 = (chunk_base + cc) * ring_per_chunk;
+            int slot = c_slot;
+            uint32_t ring_phase = c_phase;
             for (int k = 0; k < ring_per_chunk; ++k) {
-              const long long sidx = s0 + k;
-              const int slot = static_cast<int>(sidx % p.ring_slots);
-              const uint32_t ring_phase = static_cast<uint32_t>((sidx / p.ring_slots) & 1);
-              mbar_wait(smem_u32(&bar_ring_full[slot]), ring_phase);
+              if (k > 0 && ++slot == p.ring_slots) { slot = 0; ring_phase ^= 1u; }
+              mbar_wait(BAR(ring_full, slot), ring_phase);
               const uint32_t sa = ring_base + slot * p.ring_slot_bytes + lr * 128;
               if (k == 0) {
                 slot_addr = sa;
@@ -999,8 +1063,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                : "r"(sa16 + ((g ^ s3) << 4)));
                   float f8[8];
                   unpack16x8(u4, p.is_bf16, f8);
+                  // inverse LeakyReLU: f < 0 ? ns * f : f  ==  min(f, ns * f) for ns >= 1 (max for ns < 1)
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[8 * g + i] += f8[i] < 0.f ? f8[i] * ns : f8[i];
+                  for (int i = 0; i < 8; i += 2) {
+                    float m0, m1;
+                    mul2s(m0, m1, f8[i], f8[i + 1], ns);
+                    if (ns >= 1.f) add2(v[8 * g + i], v[8 * g + i + 1], fminf(f8[i], m0), fminf(f8[i + 1], m1));
+                    else add2(v[8 * g + i], v[8 * g + i + 1], fmaxf(f8[i], m0), fmaxf(f8[i + 1], m1));
+                  }
                 }
               } else if (k < ring_in) {
 #pragma unroll
@@ -1009,19 +1079,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                : "=f"(r4.x), "=f"(r4.y), "=f"(r4.z), "=f"(r4.w)
                                : "r"(sa + ((g ^ sw7) << 4)));
-                  v[4 * g + 0] += r4.x; v[4 * g + 1] += r4.y; v[4 * g + 2] += r4.z; v[4 * g + 3] += r4.w;
+                  add2(v[4 * g + 0], v[4 * g + 1], r4.x, r4.y);
+                  add2(v[4 * g + 2], v[4 * g + 3], r4.z, r4.w);
                 }
               }
               if (k > 0 || !out_f32) {
                 // slot only read: release it right away
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_ring_empty[slot]));
+                if (lane == 0) mbar_arrive(BAR(ring_empty, slot));
               }
             }
           }
           if (p.out_scale != 1.f) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= p.out_scale;
+            for (int i = 0; i < 32; i += 2) mul2s(v[i], v[i + 1], v[i], v[i + 1], p.out_scale);
           }
           if (p.stats != nullptr) {
             // image of this warp's 32 rows (warp-uniform: the host checks stats_rows % 32 == 0) and row validity
@@ -1061,7 +1132,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int g = 0; g < 4; ++g) {
               float w8[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) w8[i] = out_16 ? v[8 * g + i] : act_apply(v[8 * g + i], act2, p.act2_slope);
+              for (int i = 0; i < 8; ++i) w8[i] = v[8 * g + i];
+              if (!out_16) act_apply_n<8>(w8, act2, p.act2_slope);
               uint32_t w0, w1, w2, w3;
               if (bf) {
                 w0 = pack16(w8[0], w8[1], 1); w1 = pack16(w8[2], w8[3], 1);
@@ -1096,13 +1168,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             } else {
               tma_store_wait_read<0>();
             }
-            if (out_f32) mbar_arrive(smem_u32(&bar_ring_empty[first_slot]));
+            if (out_f32) mbar_arrive(BAR(ring_empty, first_slot));
           }
           __syncwarp();
         }
-        // advance (sub, ch) to this group's next chunk
+        // advance (sub, ch) and the ring position to this group's next chunk
         ch += ngrp;
         while (ch >= n_chunks) { ch -= n_chunks; ++sub; }
+        if (ring_per_chunk > 0) {
+          c_slot += ngrp * ring_per_chunk;
+          while (c_slot >= p.ring_slots) { c_slot -= p.ring_slots; c_phase ^= 1u; }
+        }
       }
     }
     if (leader) tma_store_wait_all();  // global writes complete before the CTA exits
