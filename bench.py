@@ -275,6 +275,15 @@ def main():
             h2d = noise_h.numel() * 4 + enc_h.numel() * 4
             d2h = out_h.numel() * 2
         achieved = gflop_gemm / gemm_ms if gemm_ms else None  # GFLOP / ms == TFLOP/s
+        # DRAM bytes per launch of the dominant kernel from the committed ncu pass (same batch only), else null
+        traffic = None
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "gemm_dram_traffic.json")) as f:
+                tj = json.load(f)
+            if int(tj.get("batch", -1)) == B and not args.unet_only:
+                traffic = tj["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            traffic = None
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": hib, "scaling": "weak",
@@ -291,7 +300,9 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "gemm_tc_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": achieved,
                          "peak": tf_peak, "unit": "TFLOP/s", "frac": (achieved / tf_peak) if achieved else None,
-                         "traffic": None, "peak_kind": peak_kind + " bf16_tflops_sustained",
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/gemm_dram_traffic.json)",
+                         "algorithmic_bytes_note": "tensor-bound kernel: achieved/peak are FLOP rates; see DESIGN.md 3",
+                         "peak_kind": peak_kind + " bf16_tflops_sustained",
                          "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms,
                          "share_of_step": (gemm_ms / ms_step) if gemm_ms else None,
                          "whole_step_tflops": (TOTAL_GFLOP_PER_CLIP if not args.unet_only else GFLOP_PER_CLIP["unet"]) * B / ms_step},

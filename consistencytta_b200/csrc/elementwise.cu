@@ -375,6 +375,59 @@ extern "C" int ctta_mrf_combine(const void* const* x, int32_t n_in, int64_t nume
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------- single-channel conv tail
+// A convolution with ONE output channel is a bandwidth problem, not a GEMM: as an implicit GEMM it would issue
+// taps * C / 16 tensor-core instructions per 128 pixels for one useful accumulator column.  It is restated as
+//   z[p, j] = sum_c x[p, c] * w[j, c]      (pointwise GEMM, N = taps: C / 16 instructions per 128 pixels, x read once)
+//   y[p]    = act(bias + sum_j z[p + shift_j, j])                                                   (this kernel)
+// which computes the same products and only reorders the fp32 summation.
+struct TapSumParams {
+  int ntaps;
+  short d0[CTTA_MAX_TAPS], d1[CTTA_MAX_TAPS];
+};
+__global__ void __launch_bounds__(256) tap_sum_kernel(const float* __restrict__ z, int z_ld, int n_img, int h, int w,
+                                                      const __grid_constant__ TapSumParams tp, const float* __restrict__ bias,
+                                                      int act, float* __restrict__ out, void* __restrict__ out16, int out16_dtype) {
+  const long long hw = static_cast<long long>(h) * w;
+  const long long total = hw * n_img;
+  const float b0 = bias != nullptr ? __ldg(bias) : 0.f;
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int rem = static_cast<int>(p % hw);
+    const int ph = rem / w, pw = rem - ph * w;
+    float acc = b0;
+    for (int j = 0; j < tp.ntaps; ++j) {
+      const int hh = ph + tp.d1[j], ww = pw + tp.d0[j];
+      if (hh >= 0 && hh < h && ww >= 0 && ww < w)
+        acc += __ldg(z + (p + static_cast<long long>(tp.d1[j]) * w + tp.d0[j]) * z_ld + j);
+    }
+    if (act == CTTA_ACT_TANH) acc = tanhf(acc);
+    else if (act == CTTA_ACT_SILU) acc = acc / (1.f + __expf(-acc));
+    if (out) out[p] = acc;
+    if (out16) reinterpret_cast<unsigned short*>(out16)[p] = cvt16e(acc, out16_dtype);
+  }
+}
+
+extern "C" int ctta_tap_sum(const float* z, int32_t z_ld, int32_t n_img, int32_t h, int32_t w, int32_t ntaps,
+                            const int16_t* tap_d0, const int16_t* tap_d1, const float* bias, int32_t act, float* out,
+                            void* out16, int32_t out16_dtype, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  CTTA_REQUIRE(z && tap_d0 && tap_d1 && (out || out16), "tap_sum: null argument");
+  CTTA_REQUIRE(ntaps >= 1 && ntaps <= CTTA_MAX_TAPS && z_ld >= ntaps && n_img >= 1 && h >= 1 && w >= 1,
+               "tap_sum: bad geometry (ntaps=%d z_ld=%d n_img=%d h=%d w=%d)", ntaps, z_ld, n_img, h, w);
+  CTTA_REQUIRE(act == CTTA_ACT_NONE || act == CTTA_ACT_TANH || act == CTTA_ACT_SILU, "tap_sum: unsupported activation");
+  TapSumParams tp{};
+  tp.ntaps = ntaps;
+  for (int j = 0; j < ntaps; ++j) {
+    tp.d0[j] = tap_d0[j];
+    tp.d1[j] = tap_d1[j];
+  }
+  const long long total = static_cast<long long>(n_img) * h * w;
+  tap_sum_kernel<<<grid_for(total, 256), 256, 0, stream>>>(z, z_ld, n_img, h, w, tp, bias, act, out, out16, out16_dtype);
+  CTTA_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int ctta_cfg_mix(const float* x, int64_t half_numel, float s, float* y, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   CTTA_REQUIRE(x && y && half_numel > 0, "cfg_mix: bad arguments");

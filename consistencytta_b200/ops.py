@@ -160,6 +160,49 @@ def pack_conv_transpose1d(weight, bias, stride, padding, dtype=None):
     return phases
 
 
+class SingleChannelConv:
+    """A conv with ONE output channel, restated as a pointwise GEMM over the taps + a shifted sum (see ctta_tap_sum)."""
+
+    def __init__(self, pw, d0, d1, bias, fold, n_pad):
+        self.pw = pw            # PackedWeight of the pointwise GEMM (block diagonal over `fold` consecutive pixels), no bias
+        self.fold = fold        # pixels per GEMM row: [rows, C] is read as [rows / fold, fold * C]
+        self.n_pad = n_pad      # taps zero padded to 8 / 16 = row pitch of z
+        self.d0 = (C.c_int16 * len(d0))(*d0)
+        self.d1 = (C.c_int16 * len(d1))(*d1)
+        self.ntaps = len(d0)
+        self.bias = bias        # fp32 [1] or None
+
+
+def pack_single_channel_conv(weight, bias=None, dilation=1, dtype=None):
+    """nn.Conv1d [1, C, k] / nn.Conv2d [1, C, kh, kw] weight ('same' padding, stride 1) -> SingleChannelConv."""
+    w = weight.detach().float()
+    assert w.shape[0] == 1
+    if w.dim() == 3:
+        k = w.shape[2]
+        taps = w[0].t().contiguous()                                        # [k, C]
+        d0 = [(j - (k - 1) // 2) * dilation for j in range(k)]
+        d1 = [0] * k
+    else:
+        kh, kw = w.shape[2], w.shape[3]
+        taps = w[0].permute(1, 2, 0).reshape(kh * kw, w.shape[1]).contiguous()  # [(kh, kw), C]
+        d1 = [i - (kh - 1) // 2 for i in range(kh) for _ in range(kw)]
+        d0 = [j - (kw - 1) // 2 for _ in range(kh) for j in range(kw)]
+    n_pad = 8 if len(d0) <= 8 else 16
+    assert len(d0) <= 16
+    # `fold` consecutive pixels form one GEMM row (the same memory, read as [rows / fold, fold * C]) against a block
+    # diagonal weight, so that N = fold * n_pad = 32 reaches the TMA-staged epilogue with M super-tiles: z[p, j] lands
+    # at the same address, and a 128-row tile carries 4x / 2x the pixels for the same number of tensor-core instructions
+    fold = 32 // n_pad
+    c = taps.shape[1]
+    tp = torch.zeros(n_pad, c, device=w.device)
+    tp[:taps.shape[0]] = taps
+    wf = torch.zeros(fold * n_pad, fold * c, device=w.device)
+    for i in range(fold):
+        wf[i * n_pad:(i + 1) * n_pad, i * c:(i + 1) * c] = tp
+    pw = pack_linear(wf, None, dtype=dtype)
+    return SingleChannelConv(pw, d0, d1, _bias(bias, 1, w.device), fold, n_pad)
+
+
 # ------------------------------------------------------------------------------------------------ GEMM
 def gemm(a, pw, mode=A_ROWS, n_img=1, h=1, w=None, rows_per_img=None, a_ld=None, out=None, out_ld=None,
          out_rows_per_img=None, residual=None, res_ld=None, rowadd=None, rowadd_rows=1, act=ACT_NONE, act_slope=0.0,
@@ -259,6 +302,28 @@ def conv1d(a, pw, rows_per_img=None, out_rows_per_img=None, **kw):
     rp = rows_per_img if rows_per_img is not None else t
     return gemm(a, pw, mode=A_CONV1D, n_img=b, h=1, w=t, rows_per_img=rp,
                 out_rows_per_img=out_rows_per_img if out_rows_per_img is not None else rp, a_ld=a.stride(1), **kw)
+
+
+def single_channel_conv(a, sc, n_img, h, w, act=ACT_NONE, out=None, out16=None):
+    """a: 16-bit channels-last [n_img, h, w, C] (h = 1 for sequences).  Returns fp32 `out` [n_img * h * w] (and / or
+    its 16-bit copy `out16`)."""
+    rows = n_img * h * w
+    assert a.is_contiguous() and rows % sc.fold == 0, "single_channel_conv: pixel count must be a multiple of the fold"
+    a2 = a.reshape(rows // sc.fold, sc.fold * a.shape[-1])
+    z = torch.empty(rows, sc.n_pad, device=a.device, dtype=torch.float32)
+    linear(a2, sc.pw, out=z.view(rows // sc.fold, sc.fold * sc.n_pad))
+    if out is None and out16 is None:
+        out = torch.empty(rows, device=a.device, dtype=torch.float32)
+    tap_sum(z, sc, n_img, h, w, act, out, out16)
+    return out if out is not None else out16
+
+
+def tap_sum(z, sc, n_img, h, w, act=ACT_NONE, out=None, out16=None):
+    """y[p] = act(bias + sum_j z[p + shift_j, j]) over the taps of `sc` (zero outside each h x w image)."""
+    check(lib().ctta_tap_sum(_ptr(z), sc.n_pad, n_img, h, w, sc.ntaps, sc.d0, sc.d1,
+                             _ptr(sc.bias) if sc.bias is not None else None, act, _ptr(out) if out is not None else None,
+                             _ptr(out16) if out16 is not None else None, _DT[out16.dtype] if out16 is not None else 0,
+                             _stream()))
 
 
 def bmm_nt(a, b, bias=None, out=None):

@@ -25,11 +25,19 @@ WAVE_SAMPLES = 163872  # 1024 mel frames through ups 5*4*2*2*2 with odd (k - s) 
 
 
 class SingleStepEngine:
-    def __init__(self, unet, vae, scheduler=None, use_graphs=True):
+    """One bucket of static buffers + one CUDA graph per (batch, text length, sigma, post-CFG, stage) key.
+
+    `max_batch` bounds the clips resident in one pass (about 0.47 GB of activations per clip at the widest point, so 64
+    clips = 30 GB): larger requests run as micro-batches through the same graphs and are stitched together, with the
+    batch-GLOBAL waveform centring of `vocoder_infer` (hifigan/utilities.py:84-86) applied over the whole request, so
+    the int16 result does not depend on how the request was split."""
+
+    def __init__(self, unet, vae, scheduler=None, use_graphs=True, max_batch=64):
         self.unet = unet
         self.vae = vae
         self.scheduler = scheduler or HeunDiscreteScheduler.from_pretrained()
         self.use_graphs = use_graphs
+        self.max_batch = max_batch
         self._graphs = {}
 
     # -------------------------------------------------------------------------------------------- hot path
@@ -113,6 +121,8 @@ class SingleStepEngine:
             timestep = float(self.scheduler.timesteps[0])
             sigma = float(self.scheduler.init_noise_sigma)
         b = noise.shape[0]
+        if self.max_batch and b > self.max_batch:
+            return self._run_micro_batches(noise, enc, mask, guidance, guidance_post, timestep, sigma, use_ema, stages)
         ent = self._bucket(b, enc.shape[1], sigma, guidance_post, use_ema, stages, dev)
         io = ent["io"]
         self.fill_inputs(io, noise, enc, mask, guidance, timestep)
@@ -138,6 +148,40 @@ class SingleStepEngine:
             out["wav"] = io["wav_ref"]
             out["int16"] = io["i16"]
         out["launches"] = ent.get("launches")
+        return out
+
+
+    def _run_micro_batches(self, noise, enc, mask, guidance, guidance_post, timestep, sigma, use_ema, stages):
+        """run() for more clips than `max_batch`: slices of at most max_batch clips reuse the per-size graphs."""
+        dev = self.unet.device
+        b = noise.shape[0]
+        cf = guidance_post > 1.0   # enc / mask / guidance rows are [unconditional ; conditional] then
+        out = {"latent": torch.empty((b,) + LATENT_SHAPE, device=dev, dtype=torch.float32), "launches": 0}
+        if stages in ("vae", "all"):
+            out["mel"] = torch.empty(b, 1, 1024, 64, device=dev, dtype=torch.float32)
+        if stages == "all":
+            out["wav"] = torch.empty(b, WAVE_SAMPLES, device=dev, dtype=torch.float32)
+
+        def rows(t, lo, hi):
+            if t is None or not torch.is_tensor(t) or t.dim() == 0 or t.shape[0] == 1:
+                return t
+            if cf and t.shape[0] == 2 * b:
+                return torch.cat([t[lo:hi], t[b + lo:b + hi]])
+            return t[lo:hi]
+
+        for lo in range(0, b, self.max_batch):
+            hi = min(lo + self.max_batch, b)
+            g = guidance.reshape(-1) if torch.is_tensor(guidance) else guidance
+            part = self.run(noise[lo:hi], rows(enc, lo, hi), rows(mask, lo, hi), rows(g, lo, hi), guidance_post,
+                            timestep, sigma, use_ema, stages)
+            out["latent"][lo:hi].copy_(part["latent"])
+            if "mel" in out:
+                out["mel"][lo:hi].copy_(part["mel"])
+            if "wav" in out:
+                out["wav"][lo:hi].copy_(part["wav"])
+            out["launches"] += part.get("launches") or 0
+        if stages == "all":
+            out["int16"], _ = ops.wave_to_int16(out["wav"])   # centring over the WHOLE request
         return out
 
 

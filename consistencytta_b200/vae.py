@@ -44,7 +44,8 @@ class Generator(PackedModule):
                                                                  sd["resblocks.%d.convs1.%d.bias" % (n, m)], dilation=d)
                     pk["rb.%d.c2.%d" % (n, m)] = ops.pack_conv1d(sd["resblocks.%d.convs2.%d.weight" % (n, m)],
                                                                  sd["resblocks.%d.convs2.%d.bias" % (n, m)], dilation=1)
-        pk["conv_post"] = ops.pack_conv1d(sd["conv_post.weight"], sd["conv_post.bias"])
+        # one output channel: pointwise GEMM over the 7 taps + shifted sum (ops.single_channel_conv)
+        pk["conv_post"] = ops.pack_single_channel_conv(sd["conv_post.weight"], sd["conv_post.bias"])
         return pk
 
     def out_length(self, t):
@@ -90,9 +91,9 @@ class Generator(PackedModule):
                     cur = dst
             # x = (sum_j resblock_j(x)) / 3 (models.py:108-112), then LeakyReLU of models.py:104 / :113 (default slope)
             cur16 = ops.mrf_combine(branch, slope, 1.0 / nk, 0.01 if last else 0.1, out=tmp16)
-        wav = torch.empty(b, t, 1, device=dev, dtype=torch.float32)
-        ops.conv1d(cur16, pk["conv_post"], out=wav, act=ACT_TANH)  # models.py:113-115
-        return wav.view(b, t)
+        wav = torch.empty(b, t, device=dev, dtype=torch.float32)
+        ops.single_channel_conv(cur16, pk["conv_post"], b, 1, t, act=ACT_TANH, out=wav)  # models.py:113-115
+        return wav
 
     def forward(self, x):
         """Reference signature: x [B, num_mels, T] fp32 -> [B, 1, T_out]."""
@@ -119,7 +120,9 @@ class Decoder(PackedModule):
             if k.endswith(".weight"):
                 name = k[:-7]
                 w = sd[k]
-                if w.dim() == 4:
+                if w.dim() == 4 and w.shape[0] == 1:   # conv_out 128 -> 1: pointwise GEMM over the 9 taps + shifted sum
+                    pk[name] = ops.pack_single_channel_conv(w, sd[name + ".bias"])
+                elif w.dim() == 4:
                     pk[name] = ops.pack_conv2d(w, sd[name + ".bias"])
                     if name.endswith(".upsample.conv"):
                         pk[name + ".up2x"] = ops.pack_upsample2x_conv2d(w, sd[name + ".bias"])
@@ -214,7 +217,7 @@ class Decoder(PackedModule):
         bb, hh, ww, _ = x.shape
         del x
         out = torch.empty(bb, hh, ww, 1, device=dev, dtype=torch.float32)
-        ops.conv2d(a, pk["conv_out"], out=out, out2=out16)
+        ops.single_channel_conv(a, pk["conv_out"], bb, hh, ww, out=out, out16=out16)  # modules.py:680
         return out
 
     def forward(self, z):

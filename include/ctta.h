@@ -213,6 +213,15 @@ int ctta_lrelu_cast(const float* x, int64_t numel, float slope, void* y, int32_t
 int ctta_mrf_combine(const void* const* x, int32_t n_in, int64_t numel, int32_t dtype, float in_slope, float out_scale,
                      float out_slope, void* y, void* stream);
 
+/* Tail of a single-output-channel convolution (AudioLDM VAE conv_out 128 -> 1, 3x3:
+ * audioldm/variational_autoencoder/modules.py:680; HiFi-GAN conv_post 32 -> 1, k = 7, + tanh:
+ * audioldm/hifigan/models.py:114-115).  The convolution is restated as a pointwise GEMM z[p, j] = x[p, :] . w[j, :]
+ * (ctta_gemm, CTTA_A_ROWS, n = taps) followed by y[p] = act(bias + sum_j z[p + (d1_j, d0_j), j]) with zero padding
+ * outside the h x w image.  z: fp32 [n_img * h * w, z_ld]; out fp32 and / or out16 (16-bit, out16_dtype) [n_img*h*w]. */
+int ctta_tap_sum(const float* z, int32_t z_ld, int32_t n_img, int32_t h, int32_t w, int32_t ntaps,
+                 const int16_t* tap_d0, const int16_t* tap_d1, const float* bias, int32_t act, float* out, void* out16,
+                 int32_t out16_dtype, void* stream);
+
 /* (1 - s) * uncond + s * cond on the two batch halves (models/audio_consistency_model.py:453-456). */
 int ctta_cfg_mix(const float* x, int64_t half_numel, float s, float* y, void* stream);
 

@@ -189,7 +189,8 @@ def test_bmm_nt_batched_weights():
 
 @pytest.mark.parametrize("mode,c,k", [("conv2d", 128, 3), ("conv1d", 32, 7), ("conv1d", 64, 3)])
 def test_single_output_channel_conv(mode, c, k):
-    """n == 1 multi-tap convolutions (VAE conv_out, HiFi-GAN conv_post + tanh) (direct-epilogue tcgen05 path; a CUDA-core reduction kernel was tried and was slower)."""
+    """n == 1 multi-tap convolutions (VAE conv_out, HiFi-GAN conv_post + tanh) through the generic implicit-GEMM path (direct-epilogue tcgen05; the models use the pointwise-GEMM + tap-sum
+    restatement tested below)."""
     torch.manual_seed(34)
     if mode == "conv2d":
         n, h, w = 3, 96, 64
@@ -210,6 +211,35 @@ def test_single_output_channel_conv(mode, c, k):
         out = torch.full((bsz, t, 1), float("nan"), device=DEV)
         ops.conv1d(x.permute(0, 2, 1).contiguous().to(DT), ops.pack_conv1d(wt, b), out=out, act=ops.ACT_TANH)
         assert rel(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("mode,c,k,dil", [("conv2d", 128, 3, 1), ("conv1d", 32, 7, 1), ("conv1d", 64, 3, 1),
+                                          ("conv1d", 32, 11, 3), ("conv2d", 48, 3, 1)])
+def test_single_channel_conv_as_pointwise_gemm_plus_tap_sum(mode, c, k, dil):
+    """The product path for n == 1 convolutions: z = x . w_taps (pointwise tcgen05 GEMM, N = taps) then
+    y[p] = act(bias + sum_j z[p + shift_j, j]) (ctta_tap_sum), against F.conv1d / F.conv2d with zero padding."""
+    torch.manual_seed(35)
+    if mode == "conv2d":
+        n, h, w = 3, 96, 64
+        x = r16(torch.randn(n, c, h, w, device=DEV))
+        wt = r16(torch.randn(1, c, k, k, device=DEV) / math.sqrt(k * k * c))
+        b = torch.randn(1, device=DEV)
+        ref = F.conv2d(x, wt, b, padding=k // 2).permute(0, 2, 3, 1)
+        out = torch.full((n, h, w, 1), float("nan"), device=DEV)
+        out16 = torch.empty(n, h, w, 1, device=DEV, dtype=DT)
+        sc = ops.pack_single_channel_conv(wt, b)
+        ops.single_channel_conv(x.permute(0, 2, 3, 1).contiguous().to(DT), sc, n, h, w, out=out, out16=out16)
+        assert rel(out, ref) < 2e-5 and rel(out16, ref) < 1e-3
+    else:
+        bsz, t = 3, 5004
+        x = r16(torch.randn(bsz, c, t, device=DEV))
+        wt = r16(torch.randn(1, c, k, device=DEV) / math.sqrt(k * c))
+        b = torch.randn(1, device=DEV)
+        ref = torch.tanh(F.conv1d(x, wt, b, padding=dil * (k // 2), dilation=dil)).permute(0, 2, 1)
+        out = torch.full((bsz, t), float("nan"), device=DEV)
+        sc = ops.pack_single_channel_conv(wt, b, dilation=dil)
+        ops.single_channel_conv(x.permute(0, 2, 1).contiguous().to(DT), sc, bsz, 1, t, act=ops.ACT_TANH, out=out)
+        assert rel(out.view(bsz, t, 1), ref) < 2e-5
 
 
 @pytest.mark.parametrize("n,h,w,c,cout", [(2, 256, 16, 64, 128), (2, 64, 4, 96, 256), (3, 128, 8, 64, 128),

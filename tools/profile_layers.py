@@ -53,12 +53,12 @@ def main():
                 "res": k.get("residual") is not None}
 
     def d_generic(*a, **k):
-        t = a[0]
+        t = a[0][0] if isinstance(a[0], (list, tuple)) else a[0]
         return {"numel": t.numel(), "shape": list(t.shape)}
 
     orig = {}
     for name in ("gemm", "groupnorm_stats", "groupnorm_apply", "layernorm", "attention", "softmax_rows", "im2col_s2",
-                 "small_linear", "wave_to_int16", "nchw_to_nhwc", "nhwc_to_nchw", "time_features"):
+                 "small_linear", "wave_to_int16", "nchw_to_nhwc", "nhwc_to_nchw", "time_features", "tap_sum", "mrf_combine"):
         orig[name] = getattr(ops, name)
         setattr(ops, name, wrap(name, orig[name], d_gemm if name == "gemm" else d_generic))
     # stage markers
