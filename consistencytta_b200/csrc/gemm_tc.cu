@@ -31,7 +31,6 @@ constexpr int kBlockK = 64;                         // 64 x 16-bit = one 128-byt
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 384;                        // 3 control warps + 8 epilogue warps + the stream-mode A loader
-constexpr int kALoaderWarp = 11;
 constexpr int kSmemMaxDynamic = 232448 - 1024;     // 227 KiB minus the static barriers
 constexpr int kSmemBudget = kSmemMaxDynamic - 1024;  // minus alignment slack
 constexpr int kEpiWarp0 = 3;                         // first of the 4 epilogue math warps
@@ -96,6 +95,7 @@ struct GemmKParams {
   int w_batched;           // the W operand has one [n, K] matrix per image (batched GEMM: attention scores / P.V)
   int res16, ring_slot_bytes;
   float res_neg_scale;
+  int cw, pair, st16_bufs, st16_bytes;   // wide / paired 16-bit epilogue I/O (see the TMA-staged epilogue)
   int acc_single;          // 1: one accumulator stage (sub_tiles * block_n * 2 > 512 TMEM columns), else two
   // stream mode (multi-tap convolutions): per (channel chunk, tap group) ONE halo'd activation box is loaded into
   // the A ring and every tap of the group is a row-shifted UMMA view of it; weight chunks stream through their own
@@ -472,8 +472,8 @@ struct GemmBars {
 };
 #define BAR(field, idx) (bar_base + static_cast<uint32_t>(offsetof(GemmBars, field)) + 8u * static_cast<uint32_t>(idx))
 
-template <class Cfg>
-__global__ void __launch_bounds__(kThreads, 1)
+template <class Cfg, int NTHREADS = kThreads>
+__global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
                const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ GemmKParams p) {
@@ -533,7 +533,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ------------------------------------------------------------------ TMA producer (one lane)
     const bool leader = elect_one_sync();
     if (leader && p.stream) {
-      // weight chunks only; the halo'd activation boxes come from their own loader warp (kALoaderWarp) so that a box is
+      // weight chunks only; the halo'd activation boxes come from their own loader warp (the last warp) so that a box is
       // requested as soon as its ring slot frees up, independent of the weight ring's back-pressure
       int w_stage = 0;
       uint32_t w_phase = 0;
@@ -730,7 +730,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         umma_commit(BAR(tmem_full, acc));  // accumulator complete -> epilogue
       }
     }
-  } else if (warp == kALoaderWarp) {
+  } else if (warp == NTHREADS / 32 - 1) {
     // ------------------------------------------------------------------ stream mode: activation box loader (one lane)
     if (elect_one_sync() && p.stream) {
       int a_stage = 0;
@@ -764,8 +764,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // Streams the fp32 residual / previous-output tiles of every chunk into the ring, running ahead of the
     // epilogue math by up to ring_slots chunks.  With no inputs it only hands out free slots (pure staging).
     if (elect_one_sync() && p.epi_tma && p.ring_slots > 0) {
-      const int n_chunks = p.block_n / kChunkCols;
+      const int io_cols = kChunkCols * p.cw;
+      const int n_chunks = p.block_n / io_cols;
       const uint32_t ring_base = tiles_base + static_cast<uint32_t>(p.ring_off);
+      // shared-memory pitch of one tile row inside a slot: fp32 128 B; 16-bit 64 B (narrow / paired) or 128 B (wide)
+      const int row_pitch = p.res16 ? (p.cw == 2 ? 128 : 64) : 128;
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -782,20 +785,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int cc = 0; cc < n_chunks * p.sub_tiles; ++cc) {
           const int sub = cc / n_chunks;
           const int ch = cc - sub * n_chunks;
-          const int col = tc.n0 + ch * kChunkCols;
+          const int col = tc.n0 + ch * io_cols;
           const int srow0 = row0 + sub * kBlockM;
           for (int k = 0; k < p.ring_per_chunk; ++k) {
             mbar_wait(BAR(ring_empty, slot), phase ^ 1u);
             const uint32_t full = BAR(ring_full, slot);
             if (k < p.ring_in) {
               mbar_arrive_expect_tx(full, static_cast<uint32_t>(p.ring_slot_bytes));
-              // the fp32 residual tile: one {32 cols x 32 rows} box per epilogue warp (the box shape the stores use)
+              // the residual tile: one box per epilogue warp quarter (the box shape the stores use)
               const void* map = static_cast<const void*>(&tmap_res);
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq) {
                 const int wr = qq * 32;
-                tma_load_3d(ring_base + slot * p.ring_slot_bytes + wr * (p.res16 ? 64 : 128), map, full, col,
-                            srow0 + (wr % p.out_rows_tile_img), img0 + wr / p.out_rows_tile_img);
+                const uint32_t dst = ring_base + slot * p.ring_slot_bytes + wr * row_pitch;
+                if (p.pair) tma_load_3d(dst, map, full, 0, (srow0 + wr) >> 1, img0);
+                else tma_load_3d(dst, map, full, col, srow0 + (wr % p.out_rows_tile_img), img0 + wr / p.out_rows_tile_img);
               }
             } else {
               mbar_arrive(full);
@@ -899,10 +903,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int grp = ew >> 2;                  // chunk phase handled by this warp
     const int ngrp = p.epi_groups;
     const int lr = q * 32 + lane;             // row inside the tile
-    const int n_chunks = p.block_n / kChunkCols;
+    // 16-bit-only epilogues move their tiles in 128-byte rows: cw = 2 pairs two 32-column halves into one I/O chunk
+    // (one ring slot, one staging buffer, one store box of 64 columns); `pair` views an N = 32 tensor as
+    // [rows / 2, 64].  The TMA unit's cost is per box ROW, so 64-byte rows halve its throughput.
+    const int cw = p.cw, pair = p.pair, st16_bufs = p.st16_bufs;
+    const int io_cols = kChunkCols * cw;
+    const int n_chunks = p.block_n / io_cols;
     const int tot_chunks = n_chunks * p.sub_tiles;
     const uint32_t ring_base = tiles_base + static_cast<uint32_t>(p.ring_off);
-    const uint32_t st16_base = tiles_base + static_cast<uint32_t>(p.stage16_off) + ew * 2 * kStage16Bytes;
+    const uint32_t st16_base = tiles_base + static_cast<uint32_t>(p.stage16_off) + ew * st16_bufs * p.st16_bytes;
     float* bias_s = reinterpret_cast<float*>(smem_raw + (tiles_base - smem_u32(smem_raw)) + p.bias_off);
     const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..255
     const int sw7 = lane & 7;
@@ -916,6 +925,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int tile_slot = 0;
     uint32_t tile_phase = 0;
     int tile_adv_q = 0, tile_adv_r = 0;
+    // chunk -> warp group by GLOBAL chunk index (it * tot_chunks + cc) % ngrp, so that a chunk count that is not a
+    // multiple of the group count (4 chunks over 3 groups) still balances over consecutive tiles
+    int rot = 0;
+    const int rot_step = tot_chunks % ngrp;
     if (ring_per_chunk > 0) {
       tile_adv_q = (tot_chunks * ring_per_chunk) / p.ring_slots;
       tile_adv_r = (tot_chunks * ring_per_chunk) - tile_adv_q * p.ring_slots;
@@ -933,8 +946,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       } else {
         row0 = tc.c2 * p.W + tc.c1; img0 = tc.c3;
       }
-      // ring position of this warp's first chunk (cc = grp) and of the next tile
-      int c_slot = tile_slot + grp * ring_per_chunk;
+      // this group's first chunk of the tile, its ring position, and the ring position of the next tile
+      int cc0 = grp - rot;
+      if (cc0 < 0) cc0 += ngrp;
+      rot += rot_step;
+      if (rot >= ngrp) rot -= ngrp;
+      int c_slot = tile_slot + cc0 * ring_per_chunk;
       uint32_t c_phase = tile_phase;
       while (ring_per_chunk > 0 && c_slot >= p.ring_slots) { c_slot -= p.ring_slots; c_phase ^= 1u; }
       tile_slot += tile_adv_r;
@@ -963,18 +980,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(BAR(tmem_full, acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
-      const int last_cc = ((tot_chunks - 1 - grp) / ngrp) * ngrp + grp;  // last chunk of this group
-      if (grp >= tot_chunks) {
+      const int last_cc = cc0 < tot_chunks ? ((tot_chunks - 1 - cc0) / ngrp) * ngrp + cc0 : -1;  // last chunk of this group
+      if (cc0 >= tot_chunks) {
         // nothing to read from this accumulator stage
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(tmem_empty, acc));
       }
-      int sub = 0, ch = grp;
+      int sub = 0, ch = cc0;
       while (ch >= n_chunks) { ch -= n_chunks; ++sub; }
-      for (int cc = grp; cc < tot_chunks; cc += ngrp, ++my_ctr) {
-        const int c0 = ch * kChunkCols;
-        const int col = tc.n0 + c0;
+      for (int cc = cc0; cc < tot_chunks; cc += ngrp, ++my_ctr) {
+        const int col_io = tc.n0 + ch * io_cols;          // first column of this I/O chunk (cw halves of 32 columns)
         const int st_row = st_row0 + sub * kBlockM;
+        const uint32_t st16 = st16_base + (st16_bufs == 2 ? (my_ctr & 1) : 0) * p.st16_bytes;
+        if (st16_bufs == 1 && (out_16 || has_out2)) {
+          // single staging buffer (wide 16-bit chunks): the previous chunk's store must have read it
+          if (leader) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        uint32_t slot_addr = 0;
+        int first_slot = -1;
+#pragma unroll 1
+        for (int hf = 0; hf < cw; ++hf) {
+        const int c0 = ch * io_cols + hf * kChunkCols;
+        const int col = tc.n0 + c0;
         uint32_t u[32];
         tmem_ld_x32(t_addr + sub * p.block_n + c0, u);
         // per-row additive term (time embedding): issue the loads before waiting on TMEM / the ring
@@ -990,7 +1018,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         tmem_ld_wait();
-        if (cc == last_cc) {
+        if (cc == last_cc && hf == cw - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(tmem_empty, acc));
@@ -1013,7 +1041,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             add2(v[4 * g + 2], v[4 * g + 3], ra[g].z, ra[g].w);
           }
         }
-        const uint32_t st16 = st16_base + (my_ctr & 1) * kStage16Bytes;
         if (act == CTTA_ACT_GEGLU) {
           // 32 accumulator columns = 16 (value, gate) pairs -> 16 outputs = 32 bytes per row (unswizzled staging)
           uint32_t w[8];
@@ -1036,31 +1063,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           __syncwarp();
         } else {
           act_apply_n<32>(v, act, p.act_slope);
-          // ---- fp32 inputs from the ring (residual, previous out)
-          uint32_t slot_addr = 0;
-          int first_slot = -1;
+          // ---- inputs from the ring (residual, previous out)
           if (ring_per_chunk > 0) {
             int slot = c_slot;
             uint32_t ring_phase = c_phase;
             for (int k = 0; k < ring_per_chunk; ++k) {
               if (k > 0 && ++slot == p.ring_slots) { slot = 0; ring_phase ^= 1u; }
-              mbar_wait(BAR(ring_full, slot), ring_phase);
+              if (hf == 0) mbar_wait(BAR(ring_full, slot), ring_phase);
               const uint32_t sa = ring_base + slot * p.ring_slot_bytes + lr * 128;
               if (k == 0) {
                 slot_addr = sa;
                 first_slot = slot;
               }
               if (k < ring_in && p.res16) {
-                // 16-bit residual tile: rows of 64 B, 64-byte swizzle (the pattern of the TMA box that wrote it)
-                const uint32_t sa16 = ring_base + slot * p.ring_slot_bytes + lr * 64;
-                const int s3 = (lane >> 1) & 3;
+                // 16-bit residual tile as the TMA boxes wrote it.  Narrow chunk: rows of 64 B, 64-byte swizzle.  Wide
+                // chunk (cw = 2): rows of 128 B holding both halves, 128-byte swizzle.  Paired rows (N = 32 viewed as
+                // [rows / 2, 64]): row r lives in half (r & 1) of 128-byte row r / 2.
+                uint32_t row_addr;
+                int pc0, sx;
+                if (cw == 2) {
+                  row_addr = ring_base + slot * p.ring_slot_bytes + lr * 128;
+                  pc0 = hf * 4;
+                  sx = lane & 7;
+                } else if (pair) {
+                  row_addr = ring_base + slot * p.ring_slot_bytes + (lr >> 1) * 128;
+                  pc0 = (lane & 1) * 4;
+                  sx = (lr >> 1) & 7;
+                } else {
+                  row_addr = ring_base + slot * p.ring_slot_bytes + lr * 64;
+                  pc0 = 0;
+                  sx = (lane >> 1) & 3;
+                }
                 const float ns = p.res_neg_scale;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                   uint4 u4;
                   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                                : "=r"(u4.x), "=r"(u4.y), "=r"(u4.z), "=r"(u4.w)
-                               : "r"(sa16 + ((g ^ s3) << 4)));
+                               : "r"(row_addr + (((pc0 + g) ^ sx) << 4)));
                   float f8[8];
                   unpack16x8(u4, p.is_bf16, f8);
                   // inverse LeakyReLU: f < 0 ? ns * f : f  ==  min(f, ns * f) for ns >= 1 (max for ns < 1)
@@ -1083,7 +1123,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   add2(v[4 * g + 2], v[4 * g + 3], r4.z, r4.w);
                 }
               }
-              if (k > 0 || !out_f32) {
+              if ((k > 0 || !out_f32) && hf == cw - 1) {
                 // slot only read: release it right away
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(ring_empty, slot));
@@ -1126,8 +1166,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           if (out_16 || has_out2) {
             const bool bf = generic && (out_16 ? (p.out_dtype == CTTA_BF16) : (p.is_bf16 != 0));
-            const uint32_t dst = st16 + lane * 64;
-            const int sw3 = (lane >> 1) & 3;
+            // staging layout = the store box: see the residual tile above
+            uint32_t dst;
+            int pc0, sx;
+            if (cw == 2) {
+              dst = st16 + lane * 128;
+              pc0 = hf * 4;
+              sx = lane & 7;
+            } else if (pair) {
+              dst = st16 + (lane >> 1) * 128;
+              pc0 = (lane & 1) * 4;
+              sx = (lane >> 1) & 7;
+            } else {
+              dst = st16 + lane * 64;
+              pc0 = 0;
+              sx = (lane >> 1) & 3;
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float w8[8];
@@ -1142,11 +1196,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 w0 = pack_f16_sat(w8[0], w8[1]); w1 = pack_f16_sat(w8[2], w8[3]);
                 w2 = pack_f16_sat(w8[4], w8[5]); w3 = pack_f16_sat(w8[6], w8[7]);
               }
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((g ^ sw3) << 4)), "r"(w0), "r"(w1),
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((pc0 + g) ^ sx) << 4)), "r"(w0), "r"(w1),
                            "r"(w2), "r"(w3)
                            : "memory");
             }
           }
+        }
+        }  // hf
+        if (act != CTTA_ACT_GEGLU) {
           fence_proxy_async();
           __syncwarp();
           if (leader) {
@@ -1155,16 +1212,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // and exposes the residual's load latency once per chunk); the 16-bit staging stays double buffered
             if (out_f32) {
               const uint32_t src = ring_base + first_slot * p.ring_slot_bytes + wrow * 128;
-              if (p.accumulate) tma_reduce_add_3d(&tmap_out, src, col, st_row, st_img);  // out += tile
-              else if (p.out4d) tma_store_4d(&tmap_out, src, col, st_row % p.W, st_row / p.W, st_img);
-              else tma_store_3d(&tmap_out, src, col, st_row, st_img);
+              if (p.accumulate) tma_reduce_add_3d(&tmap_out, src, col_io, st_row, st_img);  // out += tile
+              else if (p.out4d) tma_store_4d(&tmap_out, src, col_io, st_row % p.W, st_row / p.W, st_img);
+              else tma_store_3d(&tmap_out, src, col_io, st_row, st_img);
               tma_store_commit();
             }
             if (out_16 || has_out2) {
-              if (out_16) tma_store_3d(&tmap_out, st16, col, st_row, st_img);
-              if (has_out2) tma_store_3d(&tmap_out2, st16, col, st_row, st_img);
+              const int sc = pair ? 0 : col_io, sr = pair ? (st_row >> 1) : st_row;
+              if (out_16) tma_store_3d(&tmap_out, st16, sc, sr, st_img);
+              if (has_out2) tma_store_3d(&tmap_out2, st16, sc, sr, st_img);
               tma_store_commit();
-              tma_store_wait_read<1>();  // everything but the 16-bit group just committed has finished reading smem
+              if (st16_bufs == 2) tma_store_wait_read<1>();  // all but the 16-bit group just committed have read smem
             } else {
               tma_store_wait_read<0>();
             }
@@ -1242,12 +1300,12 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // {box_cols x 32 rows x 1} box.  Transposed-conv phases write every out_stride-th row starting at first_row.
 static int make_row_tmap(CUtensorMap* m, int dtype, const void* base, long long ld, int ncols, long long first_row,
                          long long row_step, long long n_rows, long long img_rows, int n_img, int box_cols,
-                         CUtensorMapSwizzle swz) {
+                         CUtensorMapSwizzle swz, int box_rows = 32) {
   const int esz = dtype == CTTA_F32 ? 4 : 2;
   const char* b = reinterpret_cast<const char*>(base) + first_row * ld * esz;
   cuuint64_t dims[3] = {(cuuint64_t)ncols, (cuuint64_t)(n_rows > 0 ? n_rows : 1), (cuuint64_t)n_img};
   cuuint64_t strides[2] = {(cuuint64_t)(row_step * ld * esz), (cuuint64_t)(img_rows * ld * esz)};
-  cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   return make_tmap_ex(m, dtype, swz, b, 3, dims, strides, box);
 }
 
@@ -1645,6 +1703,33 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     const long long n_rows = p.rows_per_img;
     p.row_coord_shift = 0;
     const bool geglu = d->act == CTTA_ACT_GEGLU;
+    // ---- 16-bit-only epilogues: 128-byte TMA rows (the TMA unit's cost is per box row, ~3 cycles whatever its width)
+    const bool f32_out = d->out && d->out_dtype == CTTA_F32;
+    const bool io16 = !f32_out && !geglu && (!d->residual || res16) && !d->accumulate && !d->out_up_phase &&
+                      getenv("CTTA_NO_WIDE16") == nullptr;
+    p.cw = (io16 && block_n % 64 == 0) ? 2 : 1;
+    {
+      // N = 32 tensors (HiFi-GAN last stage) viewed as [rows / 2, 64]: every pitch must be exactly 32 columns
+      const void* o16 = d->out ? d->out : d->out2;
+      const int o16_ld = d->out ? d->out_ld : d->out2_ld;
+      p.pair = (io16 && p.cw == 1 && block_n == 32 && d->n == 32 && o16 != nullptr && o16_ld == 32 &&
+                (!d->residual || d->res_ld == 32) && d->a_mode != CTTA_A_CONV2D && d->out_stride == 1 && first_row % 2 == 0 &&
+                n_rows % 2 == 0 && d->out_rows_per_img % 2 == 0)
+                   ? 1 : 0;
+    }
+    p.st16_bufs = p.cw == 2 ? 1 : 2;
+    p.st16_bytes = p.cw == 2 ? 2 * kStage16Bytes : kStage16Bytes;
+    // row map of a 16-bit epilogue tensor in the layout chosen above
+    auto make_map16 = [&](CUtensorMap* m, int dtype, const void* base, long long ld) -> int {
+      if (p.pair)
+        return make_row_tmap(m, dtype, base, 64, 64, first_row / 2, 1, n_rows / 2, d->out_rows_per_img / 2, d->n_img, 64,
+                             CU_TENSOR_MAP_SWIZZLE_128B, 16);
+      if (p.cw == 2)
+        return make_row_tmap(m, dtype, base, ld, d->n, first_row, d->out_stride, n_rows, d->out_rows_per_img, d->n_img, 64,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+      return make_row_tmap(m, dtype, base, ld, d->n, first_row, d->out_stride, n_rows, d->out_rows_per_img, d->n_img,
+                           kChunkCols, CU_TENSOR_MAP_SWIZZLE_64B);
+    };
     if (d->out_up_phase) {
       // logical pixel (h, w) -> output pixel (2h + ph, 2w + pw): a warp's 32 consecutive pixels are a {wb x 32 / wb} box
       const int ph = (d->out_up_phase - 1) >> 1, pw = (d->out_up_phase - 1) & 1;
@@ -1663,25 +1748,28 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
       p.out4d = 1;
     } else if (d->out) {
       const bool f32 = d->out_dtype == CTTA_F32;
-      int rc = make_row_tmap(&tmap_out, d->out_dtype, d->out, d->out_ld, geglu ? d->n / 2 : d->n, first_row,
-                             d->out_stride, n_rows, d->out_rows_per_img, d->n_img, geglu ? 16 : kChunkCols,
-                             f32 ? CU_TENSOR_MAP_SWIZZLE_128B : (geglu ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B));
+      int rc;
+      if (f32 || geglu)
+        rc = make_row_tmap(&tmap_out, d->out_dtype, d->out, d->out_ld, geglu ? d->n / 2 : d->n, first_row, d->out_stride,
+                           n_rows, d->out_rows_per_img, d->n_img, geglu ? 16 : kChunkCols,
+                           f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+      else
+        rc = make_map16(&tmap_out, d->out_dtype, d->out, d->out_ld);
       if (rc) return rc;
     }
     if (d->out2) {
-      int rc = make_row_tmap(&tmap_out2, d->ab_dtype, d->out2, d->out2_ld, d->n, first_row, d->out_stride, n_rows,
-                             d->out_rows_per_img, d->n_img, kChunkCols, CU_TENSOR_MAP_SWIZZLE_64B);
+      int rc = make_map16(&tmap_out2, d->ab_dtype, d->out2, d->out2_ld);
       if (rc) return rc;
     }
     if (d->residual) {
-      int rc = make_row_tmap(&tmap_res, res16 ? d->res_dtype : CTTA_F32, d->residual, d->res_ld, d->n, first_row,
-                             d->out_stride, n_rows, d->out_rows_per_img, d->n_img, kChunkCols,
-                             res16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+      int rc = res16 ? make_map16(&tmap_res, d->res_dtype, d->residual, d->res_ld)
+                     : make_row_tmap(&tmap_res, CTTA_F32, d->residual, d->res_ld, d->n, first_row, d->out_stride, n_rows,
+                                     d->out_rows_per_img, d->n_img, kChunkCols, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
     p.res16 = res16 ? 1 : 0;
     p.res_neg_scale = d->res_neg_scale != 0.f ? d->res_neg_scale : 1.f;
-    const int slot_b = res16 ? kRingSlotBytes / 2 : kRingSlotBytes;
+    const int slot_b = res16 ? (p.cw == 2 ? kRingSlotBytes : kRingSlotBytes / 2) : kRingSlotBytes;
     p.ring_slot_bytes = slot_b;
     p.ring_in = d->residual ? 1 : 0;
     const bool out_f32 = d->out && d->out_dtype == CTTA_F32;
@@ -1691,7 +1779,9 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     bias_bytes = kBiasBytes;
     int stages = 0, ring = 0, groups = 2;
     // two groups of epilogue warps double the epilogue throughput but cost staging memory and ring depth; fall
-    // back to one group when that would leave fewer than 3 mainloop stages (wide, MMA-bound tiles)
+    // back to one group when that would leave fewer than 3 mainloop stages (wide, MMA-bound tiles).  (A third group in
+    // a 512-thread instance was measured on the HiFi-GAN C <= 128 convolutions: <= 5 %, they are bound by the TMA
+    // unit's request rate, not by epilogue warps.)
     for (groups = 2; groups >= 1 && stages == 0; --groups) {
       st16_bytes = need16 ? groups * 4 * 2 * kStage16Bytes : 0;
       const int budget = kSmemBudget - p.tiles_off - st16_bytes - bias_bytes;
@@ -1700,8 +1790,8 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
         if (st >= 3 || groups == 1) stages = st;
       } else {
         // every warp group holds one slot while it works on a chunk; the rest is the loader's prefetch distance
-        const int need = 2 * p.ring_per_chunk;
-        const int prefs[3] = {need > 5 ? need : 5, need > 4 ? need : 4, need > 3 ? need : 3};
+        const int need = (groups > 2 ? groups : 2) * p.ring_per_chunk;
+        const int prefs[3] = {need + 3, need + 2, need + 1};
         for (int i = 0; i < 3 && stages == 0; ++i) {
           const int st = (budget - prefs[i] * slot_b) / p.stage_bytes;
           if (st >= 3 || (groups == 1 && i == 2 && st >= 2)) {
@@ -1773,6 +1863,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
       }
     }
   }
+  const int n_threads = kThreads;
   {
     static std::mutex mu;
     static std::set<const void*> configured;
@@ -1783,7 +1874,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
       configured.insert(reinterpret_cast<const void*>(fn));
     }
   }
-  fn<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, tmap_out, tmap_out2, tmap_res, p);
+  fn<<<grid, n_threads, smem_bytes, stream>>>(tmap_a, tmap_b, tmap_out, tmap_out2, tmap_res, p);
   CTTA_LAUNCH_CHECK();
   return 0;
 }

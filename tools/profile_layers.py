@@ -54,7 +54,10 @@ def main():
 
     def d_generic(*a, **k):
         t = a[0][0] if isinstance(a[0], (list, tuple)) else a[0]
-        return {"numel": t.numel(), "shape": list(t.shape)}
+        shp = list(t.shape)
+        if len(a) > 1 and torch.is_tensor(a[1]):
+            shp = [shp, list(a[1].shape)]
+        return {"numel": t.numel(), "shape": shp}
 
     orig = {}
     for name in ("gemm", "groupnorm_stats", "groupnorm_apply", "layernorm", "attention", "softmax_rows", "im2col_s2",
@@ -82,6 +85,7 @@ def main():
     by_kernel = defaultdict(lambda: [0, 0.0])
     by_stage = defaultdict(float)
     shapes = defaultdict(lambda: {"count": 0, "ms": 0.0, "flops": 0.0})
+    other = defaultdict(lambda: {"count": 0, "ms": 0.0})
     for name, desc, s, e, st in records:
         ms = s.elapsed_time(e)
         by_kernel[name][0] += 1
@@ -93,6 +97,10 @@ def main():
             shapes[key]["count"] += 1
             shapes[key]["ms"] += ms
             shapes[key]["flops"] += desc["flops"]
+        else:
+            key = "%s %s %s" % (st, name, desc["shape"])
+            other[key]["count"] += 1
+            other[key]["ms"] += ms
     rows = sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])
     print("total eager step %.2f ms (batch %d)" % (total, args.batch))
     for k, (n, ms) in sorted(by_kernel.items(), key=lambda kv: -kv[1][1]):
@@ -102,9 +110,13 @@ def main():
     print("top gemm shapes (padded-dim TFLOP/s):")
     for k, v in rows[:args.top]:
         print("%8.3f ms x%-3d %7.1f TF/s  %s" % (v["ms"], v["count"], v["flops"] / v["ms"] / 1e9, k))
+    print("other kernels by first-argument shape:")
+    orows = sorted(other.items(), key=lambda kv: -kv[1]["ms"])
+    for k, v in orows[:args.top]:
+        print("%8.3f ms x%-3d  %s" % (v["ms"], v["count"], k))
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     json.dump({"batch": args.batch, "total_ms": total, "by_kernel": {k: v for k, v in by_kernel.items()},
-               "by_stage": by_stage, "gemm_shapes": rows}, open(args.out, "w"), indent=1)
+               "by_stage": by_stage, "gemm_shapes": rows, "other_shapes": orows}, open(args.out, "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -20,6 +20,7 @@ ap.add_argument("--w", type=int, default=16)
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--kind", default="c1", choices=["c1", "c2", "c2h", "f32res", "f16"])
 ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--seconds", type=float, default=0.0, help="sustained mode: repeat for this long first (power-capped clocks)")
 a = ap.parse_args()
 dev = "cuda"
 n = a.n or a.c
@@ -55,6 +56,13 @@ else:
 for _ in range(a.iters):
     fn(x, pw, **kw)
 torch.cuda.synchronize()
+if a.seconds > 0:   # bring the chip to its sustained (power-capped) clocks with the same kernel before timing
+    import time
+    t0 = time.time()
+    while time.time() - t0 < a.seconds:
+        for _ in range(50):
+            fn(x, pw, **kw)
+        torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.iters):
