@@ -1050,17 +1050,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const float o1 = v[4 * i + 2] * gelu_fast(v[4 * i + 3]) * p.out_scale;
             w[i] = (generic && p.out_dtype == CTTA_BF16) ? pack16(o0, o1, 1) : pack_f16_sat(o0, o1);
           }
-          const uint32_t dst = st16 + lane * 32;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
-          fence_proxy_async();
-          __syncwarp();
-          if (leader) {
-            tma_store_3d(&tmap_out, st16, col >> 1, st_row, st_img);
-            tma_store_commit();
-            tma_store_wait_read<1>();
+          if (cw > 1) {
+            // wide GEGLU chunk: cw halves of 16 outputs (32 B) fill one 128-byte staging row, 128-byte swizzle
+            const uint32_t dst = st16 + lane * 128;
+            const int sx = lane & 7;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((2 * hf) ^ sx) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((2 * hf + 1) ^ sx) << 4)), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+          } else {
+            const uint32_t dst = st16 + lane * 32;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
           }
-          __syncwarp();
         } else {
           act_apply_n<32>(v, act, p.act_slope);
           // ---- inputs from the ring (residual, previous out)
@@ -1203,7 +1203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         }  // hf
-        if (act != CTTA_ACT_GEGLU) {
+        {
           fence_proxy_async();
           __syncwarp();
           if (leader) {
@@ -1218,7 +1218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tma_store_commit();
             }
             if (out_16 || has_out2) {
-              const int sc = pair ? 0 : col_io, sr = pair ? (st_row >> 1) : st_row;
+              const int sc = pair ? 0 : (act == CTTA_ACT_GEGLU ? (col_io >> 1) : col_io), sr = pair ? (st_row >> 1) : st_row;
               if (out_16) tma_store_3d(&tmap_out, st16, sc, sr, st_img);
               if (has_out2) tma_store_3d(&tmap_out2, st16, sc, sr, st_img);
               tma_store_commit();
@@ -1708,6 +1708,8 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     const bool io16 = !f32_out && !geglu && (!d->residual || res16) && !d->accumulate && !d->out_up_phase &&
                       getenv("CTTA_NO_WIDE16") == nullptr;
     p.cw = (io16 && block_n % 64 == 0) ? 2 : 1;
+    const bool geglu_wide = geglu && block_n % 128 == 0 && getenv("CTTA_NO_WIDE16") == nullptr;
+    if (geglu_wide) p.cw = 4;   // 4 x 32 accumulator columns = 64 outputs = one 128-byte row
     {
       // N = 32 tensors (HiFi-GAN last stage) viewed as [rows / 2, 64]: every pitch must be exactly 32 columns
       const void* o16 = d->out ? d->out : d->out2;
@@ -1717,8 +1719,8 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
                 n_rows % 2 == 0 && d->out_rows_per_img % 2 == 0)
                    ? 1 : 0;
     }
-    p.st16_bufs = p.cw == 2 ? 1 : 2;
-    p.st16_bytes = p.cw == 2 ? 2 * kStage16Bytes : kStage16Bytes;
+    p.st16_bufs = p.cw >= 2 ? 1 : 2;
+    p.st16_bytes = p.cw >= 2 ? 2 * kStage16Bytes : kStage16Bytes;
     // row map of a 16-bit epilogue tensor in the layout chosen above
     auto make_map16 = [&](CUtensorMap* m, int dtype, const void* base, long long ld) -> int {
       if (p.pair)
@@ -1751,8 +1753,8 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
       int rc;
       if (f32 || geglu)
         rc = make_row_tmap(&tmap_out, d->out_dtype, d->out, d->out_ld, geglu ? d->n / 2 : d->n, first_row, d->out_stride,
-                           n_rows, d->out_rows_per_img, d->n_img, geglu ? 16 : kChunkCols,
-                           f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+                           n_rows, d->out_rows_per_img, d->n_img, geglu ? (geglu_wide ? 64 : 16) : kChunkCols,
+                           (f32 || geglu_wide) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
       else
         rc = make_map16(&tmap_out, d->out_dtype, d->out, d->out_ld);
       if (rc) return rc;

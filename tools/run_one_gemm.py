@@ -18,7 +18,7 @@ ap.add_argument("--rows", type=int, default=81936)
 ap.add_argument("--h", type=int, default=256)
 ap.add_argument("--w", type=int, default=16)
 ap.add_argument("--batch", type=int, default=64)
-ap.add_argument("--kind", default="c1", choices=["c1", "c2", "c2h", "f32res", "f16"])
+ap.add_argument("--kind", default="c1", choices=["c1", "c2", "c2h", "f32res", "f16", "geglu"])
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--seconds", type=float, default=0.0, help="sustained mode: repeat for this long first (power-capped clocks)")
 a = ap.parse_args()
@@ -49,6 +49,8 @@ elif a.kind == "c2":
 elif a.kind == "c2h":   # HiFi-GAN c2: 16-bit LeakyReLU'ed residual -> LeakyReLU'ed 16-bit operand
     kw = dict(residual=torch.randn(shape, device=dev).to(DT), res_neg_scale=10.0,
               out2=torch.empty(shape, device=dev, dtype=DT), act2=ops.ACT_LRELU, act2_slope=0.1)
+elif a.kind == "geglu":   # UNet feed-forward: interleaved (value, gate) columns -> n / 2 16-bit outputs
+    kw = dict(out=torch.empty(shape[:-1] + (n // 2,), device=dev, dtype=DT), act=ops.ACT_GEGLU)
 elif a.kind == "f32res":
     kw = dict(out=torch.empty(shape, device=dev), residual=torch.randn(shape, device=dev))
 else:
