@@ -18,7 +18,7 @@ import torch  # noqa: E402
 from consistencytta_b200 import ops  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("what", choices=["attention", "gn_apply", "gn_stats", "layernorm"])
+ap.add_argument("what", choices=["attention", "gn_apply", "gn_stats", "layernorm", "tap_sum", "mrf_combine"])
 ap.add_argument("--b", type=int, default=64)
 ap.add_argument("--heads", type=int, default=5)
 ap.add_argument("--lq", type=int, default=4096)
@@ -59,6 +59,20 @@ elif a.what in ("gn_apply", "gn_stats"):
     else:
         fn = lambda: ops.groupnorm_stats(x, 32, stats=st)
         work = x.numel() * x.element_size()
+    unit, scale = "GB/s", 1e6
+elif a.what == "tap_sum":   # VAE conv_out tail: 9 taps of a [n, h, w, 16] fp32 partial-product tensor
+    sc = ops.pack_single_channel_conv(torch.randn(1, a.c, 3, 3, device=dev), torch.randn(1, device=dev))
+    z = torch.randn(a.n * a.h * a.w, sc.n_pad, device=dev)
+    y = torch.empty(a.n * a.h * a.w, device=dev)
+    y16 = torch.empty(a.n * a.h * a.w, device=dev, dtype=DT)
+    fn = lambda: ops.tap_sum(z, sc, a.n, a.h, a.w, ops.ACT_NONE, y, y16)
+    work = z.shape[0] * (9 * 4 + 4 + 2)     # the 9 taps that are summed + both outputs
+    unit, scale = "GB/s (algorithmic)", 1e6
+elif a.what == "mrf_combine":   # HiFi-GAN stage sum: 3 x 16-bit in, 16-bit out
+    xs = [torch.randn(a.n, a.rows, a.c, device=dev).to(DT) for _ in range(3)]
+    y = torch.empty_like(xs[0])
+    fn = lambda: ops.mrf_combine(xs, 0.1, 1.0 / 3, 0.1, out=y)
+    work = xs[0].numel() * 8
     unit, scale = "GB/s", 1e6
 else:
     ld = ops.round_up(a.d, 64)
