@@ -1,9 +1,10 @@
 // Implicit-GEMM convolution / linear kernel for sm_100a.
 //
-//   * one persistent CTA per SM, 7 warps: warp 0 = TMA producer (A/W tiles), warp 1 = tcgen05.mma issuer + TMEM
+//   * one persistent CTA per SM, 12 warps: warp 0 = TMA producer (A/W tiles), warp 1 = tcgen05.mma issuer + TMEM
 //     owner, warp 2 = epilogue loader (TMA-prefetches residual / accumulate tiles into a shared-memory ring so
-//     their latency hides behind the mainloop), warps 3..6 = epilogue math (TMEM -> registers -> swizzled shared
-//     memory -> TMA store: every global access of the epilogue is a full-line bulk transfer)
+//     their latency hides behind the mainloop), warps 3..10 = two groups of epilogue math warps (TMEM -> registers
+//     -> swizzled shared memory -> TMA store: every global access of the epilogue is a full-line bulk transfer),
+//     warp 11 = activation-box loader of the stream mainloop
 //   * A (activations, channels-last) is never im2col'ed: for filter tap j the producer issues a tiled TMA load
 //     of the 128-pixel box shifted by (dh_j, dw_j); TMA's out-of-bounds zero fill IS the conv zero padding.
 //     The landed box is 128 rows x 64 channels x 16 bit = rows of 128 B with the 128-byte swizzle, i.e. the
@@ -38,7 +39,6 @@ constexpr int kChunkCols = 32;                       // accumulator columns per 
 constexpr int kRingSlotBytes = kBlockM * kChunkCols * 4;  // 16 KiB: 128 rows x 32 fp32 columns (128-B swizzle)
 constexpr int kMaxRing = 8;
 constexpr int kStage16Bytes = 32 * kChunkCols * 2;   // 2 KiB: 32 rows x 32 16-bit columns per warp per buffer
-constexpr int kEpiWarps = 8;                         // two warps per TMEM lane quarter, alternating chunks
 constexpr int kBiasBytes = 2 * 256 * 4;
 
 struct GemmKParams {

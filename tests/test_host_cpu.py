@@ -151,3 +151,25 @@ def test_audiolcm_load_pretrained_key_remap():
     assert (m.student_target_unet.conv_in.bias == 3.0).all()
     assert (m.student_ema_unet.conv_in.bias == 3.0).all()            # no slow EMA -> copy of the EMA weights
     m.check_eval_mode()
+
+
+def test_bench_reference_arm_line_and_nonzero_rank_exit():
+    """`bench.py --impl reference` (the CPU oracle port timed on the host cores): rank 0 prints ONE JSON line with the
+    contract's keys; under torchrun every other rank exits 0 without work."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--text-len", "8"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0

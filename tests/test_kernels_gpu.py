@@ -42,9 +42,10 @@ def test_linear(m, k, n):
     assert rel(out16, a @ w.t() + b) < 1e-3
 
 
-def test_linear_geglu():
+@pytest.mark.parametrize("m,k,d", [(500, 256, 1024), (300, 128, 48), (1000, 320, 640)])
+def test_linear_geglu(m, k, d):
+    """GEGLU epilogue: 64-output (128-byte) store rows when the N tile is a multiple of 128, 16-output rows otherwise."""
     torch.manual_seed(1)
-    m, k, d = 500, 256, 1024
     a = r16(torch.randn(m, k, device=DEV))
     w = r16(torch.randn(2 * d, k, device=DEV) / math.sqrt(k))
     b = torch.randn(2 * d, device=DEV)
@@ -152,7 +153,9 @@ def test_conv_transpose1d(k, s, cin, cout, t, bsz):
 
 
 @pytest.mark.parametrize("k,dil,c,t,bsz", [(3, 1, 32, 1000, 2), (7, 3, 64, 2500, 3), (11, 5, 128, 40968, 3),
-                                           (11, 1, 256, 20484, 4), (7, 1, 512, 5121, 8), (3, 5, 32, 163872, 4)])
+                                           (11, 1, 256, 20484, 4), (7, 1, 512, 5121, 8), (3, 5, 32, 163872, 4),
+                                           # odd row count: N = 32 cannot be viewed as [rows / 2, 64] (64-byte-row fallback)
+                                           (3, 1, 32, 1001, 2), (7, 1, 96, 777, 2)])
 def test_conv1d_lrelu_residual_stream(k, dil, c, t, bsz):
     """HiFi-GAN ResBlock pair with the activation held only as lx = lrelu(x): c2's epilogue adds the residual recovered
     from lx (negative values * 1/slope) and emits lrelu(x') again (16-bit residual ring + inverse LeakyReLU)."""
