@@ -20,6 +20,7 @@
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <set>
 #include "ctta_internal.h"
@@ -96,6 +97,9 @@ struct GemmKParams {
   int res16, ring_slot_bytes;
   float res_neg_scale;
   int cw, pair, st16_bufs, st16_bytes;   // wide / paired 16-bit epilogue I/O (see the TMA-staged epilogue)
+  // stream mode in CTA pairs (cluster of 2): the two CTAs work on neighbouring M tiles of the SAME N tile in lock step;
+  // each loads half of every weight chunk and TMA-multicasts it to both, halving the weight bytes an SM pulls from L2
+  int w_mcast, total_tiles_mc;
   int acc_single;          // 1: one accumulator stage (sub_tiles * block_n * 2 > 512 TMEM columns), else two
   // stream mode (multi-tap convolutions): per (channel chunk, tap group) ONE halo'd activation box is loaded into
   // the A ring and every tap of the group is a row-shifted UMMA view of it; weight chunks stream through their own
@@ -120,7 +124,15 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile)
   TileCoord tc;
   int m_tile = tile;
   tc.n0 = 0;
-  if (p.n_tiles_n != 1) {   // (one N tile: no division on the per-tile path of the narrow convolutions)
+  if (p.w_mcast) {
+    // tile = 2 * (pair index q) + half: the CTAs of a pair (consecutive block indices) share q, hence the N tile, and
+    // take M tiles 2 * (q / n_tiles_n) + half.  M tiles past the end decode to an out-of-range image: their loads are
+    // zero-filled and their stores clipped by the TMA unit, so a pair always runs the same number of tiles.
+    const int half = tile & 1, q = tile >> 1;
+    const int qm = q / p.n_tiles_n;
+    tc.n0 = (q - qm * p.n_tiles_n) * p.block_n;
+    m_tile = 2 * qm + half;
+  } else if (p.n_tiles_n != 1) {   // (one N tile: no division on the per-tile path of the narrow convolutions)
     m_tile = tile / p.n_tiles_n;
     tc.n0 = (tile - m_tile * p.n_tiles_n) * p.block_n;
   }
@@ -492,7 +504,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(BAR(full, s), 1);
-      mbar_init(BAR(empty, s), 1);
+      mbar_init(BAR(empty, s), p.w_mcast ? 2 : 1);   // pair mode: a weight stage is released by both CTAs' MMA warps
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(tmem_full, s), 1);
@@ -523,9 +535,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.w_mcast) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into them
   const uint32_t tmem_base = tmem_base_slot;
 
-  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int total_tiles = p.w_mcast ? p.total_tiles_mc : p.n_tiles_m * p.n_tiles_n;
   const int k_iters = p.ntaps * p.k_chunks;
 
   const uint32_t stages_base = tiles_base + static_cast<uint32_t>(p.tiles_off);
@@ -538,6 +551,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int w_stage = 0;
       uint32_t w_phase = 0;
       const uint32_t w_base = tiles_base + static_cast<uint32_t>(p.w_ring_off);
+      const uint32_t mc_rank = p.w_mcast ? cluster_ctarank() : 0u;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -545,8 +559,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_wait(BAR(empty, w_stage), w_phase ^ 1u);
             const uint32_t wfull = BAR(full, w_stage);
             mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(p.w_stage_bytes));
-            tma_load_2d(w_base + w_stage * p.w_stage_bytes, &tmap_b, wfull, (p.tap_id[j] * p.k_chunks + kc) * kBlockK,
-                        tc.n0);
+            if (p.w_mcast) {
+              // this CTA's half of the chunk (block_n / 2 weight rows) goes to both CTAs of the pair
+              tma_load_2d_mcast(w_base + w_stage * p.w_stage_bytes + mc_rank * (p.w_stage_bytes >> 1), &tmap_b, wfull,
+                                (p.tap_id[j] * p.k_chunks + kc) * kBlockK, tc.n0 + static_cast<int>(mc_rank) * (p.block_n >> 1),
+                                static_cast<uint16_t>(3));
+            } else {
+              tma_load_2d(w_base + w_stage * p.w_stage_bytes, &tmap_b, wfull, (p.tap_id[j] * p.k_chunks + kc) * kBlockK,
+                          tc.n0);
+            }
             if (++w_stage == p.n_stages) {
               w_stage = 0;
               w_phase ^= 1u;
@@ -647,7 +668,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   umma_chunk_n(nkk, d_tmem + sub * p.block_n, a_lo + sub * (kBlockM * 8), b_lo, idesc, started);
               }
               started = 1;
-              umma_commit(BAR(empty, w_stage));
+              if (p.w_mcast) umma_commit_mcast(BAR(empty, w_stage), static_cast<uint16_t>(3));
+              else umma_commit(BAR(empty, w_stage));
               if (++w_stage == p.n_stages) {
                 w_stage = 0;
                 w_phase ^= 1u;
@@ -1147,6 +1169,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               s_img = (p.a_mode == CTTA_A_ROWS) ? (row0 + sub * kBlockM + wrow) / p.stats_rows : img0;
               if (p.a_mode == CTTA_A_ROWS && !(row0 + sub * kBlockM + wrow < p.rows_per_img)) s_img = 0;  // all lanes invalid
             }
+            if (s_img >= p.n_img && p.a_mode != CTTA_A_ROWS) {   // padding tile of a CTA pair
+              rv = false;
+              s_img = 0;
+            }
             float* sdst = p.stats + static_cast<long long>(s_img) * p.stats_groups * 2;
             const int g0 = col / p.stats_cpg;
             switch (p.stats_cpg) {
@@ -1244,6 +1270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (p.w_mcast) cluster_sync_all();   // the peer may still multicast into this CTA's shared memory / barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
@@ -1827,8 +1854,20 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     p.n_stages = n_stages;
   }
   const int smem_bytes = p.tiles_off + p.n_stages * p.stage_bytes + ring_bytes + st16_bytes + bias_bytes + 1024;
-  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
+  int total_tiles = p.n_tiles_m * p.n_tiles_n;
   int grid = sm_count();
+  // ---- CTA pairs with multicast weight chunks (see GemmKParams::w_mcast): stream mode, enough tiles for every pair
+  if (p.stream && !p.w_batched && block_n >= 128 && block_n % 16 == 0 && p.n_tiles_m >= 2 && (grid % 2) == 0 &&
+      total_tiles >= 2 * grid && getenv("CTTA_NO_MCAST") == nullptr) {
+    p.w_mcast = 1;
+    p.total_tiles_mc = 2 * ((p.n_tiles_m + 1) / 2) * p.n_tiles_n;
+    total_tiles = p.total_tiles_mc;
+    cuuint64_t dims[2] = {(cuuint64_t)d->ntaps * c_pad, (cuuint64_t)d->n};
+    cuuint64_t strides[1] = {(cuuint64_t)d->ntaps * c_pad * esz};
+    cuuint32_t box[2] = {kBlockK, (cuuint32_t)(block_n / 2)};
+    int rc = make_tmap(&tmap_b, p.is_bf16, d->wgt, 2, dims, strides, box);
+    if (rc) return rc;
+  }
   if (grid > total_tiles) grid = total_tiles;
 
   // ---- pick the compile-time specialised epilogue instance (fp16 operands / outputs only), else the generic one
@@ -1875,6 +1914,40 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
                                      kSmemMaxDynamic));
       configured.insert(reinterpret_cast<const void*>(fn));
     }
+  }
+  if (p.w_mcast) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(n_threads));
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // co-resident clusters (a GPC with an odd number of free SMs cannot host a last pair): size the persistent grid to them
+    {
+      static std::mutex mu2;
+      static std::map<const void*, int> max_clusters;
+      std::lock_guard<std::mutex> lock(mu2);
+      auto itc = max_clusters.find(reinterpret_cast<const void*>(fn));
+      int n_cl = 0;
+      if (itc == max_clusters.end()) {
+        cudaLaunchConfig_t q = cfg;
+        q.dynamicSmemBytes = kSmemMaxDynamic;
+        CTTA_CUDA(cudaOccupancyMaxActiveClusters(&n_cl, fn, &q));
+        max_clusters[reinterpret_cast<const void*>(fn)] = n_cl;
+      } else {
+        n_cl = itc->second;
+      }
+      if (n_cl >= 1 && 2 * n_cl < grid) cfg.gridDim = dim3(static_cast<unsigned>(2 * n_cl));
+    }
+    CTTA_CUDA(cudaLaunchKernelEx(&cfg, fn, tmap_a, tmap_b, tmap_out, tmap_out2, tmap_res, p));
+    ::ctta::count_launch();
+    return 0;
   }
   fn<<<grid, n_threads, smem_bytes, stream>>>(tmap_a, tmap_b, tmap_out, tmap_out2, tmap_res, p);
   CTTA_LAUNCH_CHECK();
