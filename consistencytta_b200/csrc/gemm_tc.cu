@@ -602,6 +602,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = static_cast<uint32_t>(p.stage_bytes);
+      const uint32_t mc_rank = p.w_mcast ? cluster_ctarank() : 0u;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         for (int sub = 0; sub < p.sub_tiles; ++sub) {
@@ -622,7 +623,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               } else {
                 tma_load_4d(a_dst, &tmap_a, full, kc * kBlockK, tc.c1 + d0, tc.c2 + d1, tc.c3);
               }
-              if (p.w_batched) tma_load_3d(b_dst, &tmap_b, full, kb * kBlockK, tc.n0, tc.c2);
+              if (p.w_mcast)   // CTA pair: this CTA's half of the weight tile goes to both CTAs' stages
+                tma_load_2d_mcast(b_dst + mc_rank * static_cast<uint32_t>(p.block_n * 64), &tmap_b, full, kb * kBlockK,
+                                  tc.n0 + static_cast<int>(mc_rank) * (p.block_n >> 1), static_cast<uint16_t>(3));
+              else if (p.w_batched) tma_load_3d(b_dst, &tmap_b, full, kb * kBlockK, tc.n0, tc.c2);
               else tma_load_2d(b_dst, &tmap_b, full, kb * kBlockK, tc.n0);
               if (++stage == p.n_stages) {
                 stage = 0;
@@ -741,7 +745,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             umma_chunk<4>(d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
           else
             umma_chunk_n(p.kk_last, d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);  // skip all-zero K slices
-          umma_commit(BAR(empty, stage));  // frees the smem stage once these MMAs retire
+          if (p.w_mcast) umma_commit_mcast(BAR(empty, stage), static_cast<uint16_t>(3));   // both CTAs of the pair
+          else umma_commit(BAR(empty, stage));  // frees the smem stage once these MMAs retire
           if (++kc == p.k_chunks) kc = 0;
           if (++stage == p.n_stages) {
             stage = 0;
@@ -1857,7 +1862,8 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   int total_tiles = p.n_tiles_m * p.n_tiles_n;
   int grid = sm_count();
   // ---- CTA pairs with multicast weight chunks (see GemmKParams::w_mcast): stream mode, enough tiles for every pair
-  if (p.stream && !p.w_batched && block_n >= 128 && block_n % 16 == 0 && p.n_tiles_m >= 2 && (grid % 2) == 0 &&
+  const bool mc_generic = !p.stream && !p.halo && p.epi_tma && getenv("CTTA_NO_MCAST_GENERIC") == nullptr;
+  if ((p.stream || mc_generic) && !p.w_batched && block_n >= 128 && block_n % 16 == 0 && p.n_tiles_m >= 2 && (grid % 2) == 0 &&
       total_tiles >= 2 * grid && getenv("CTTA_NO_MCAST") == nullptr) {
     p.w_mcast = 1;
     p.total_tiles_mc = 2 * ((p.n_tiles_m + 1) / 2) * p.n_tiles_n;
