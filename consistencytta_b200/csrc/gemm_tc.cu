@@ -397,6 +397,33 @@ __device__ __forceinline__ void lrelu2(float& v0, float& v1, float slope) {
     v1 = fminf(v1, m1);
   }
 }
+// x = x * a + b on both halves (FFMA2), a and b pairs
+__device__ __forceinline__ void fma2(float& x0, float& x1, float a0, float a1, float b) {
+  uint64_t x, av, bv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(av) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x) : "l"(x), "l"(av), "l"(bv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+}
+// gelu_fast() of two values with the polynomial on packed pairs (same operations and roundings, half the FFMA slots)
+__device__ __forceinline__ void gelu_fast2(float g0, float g1, float& r0, float& r1) {
+  const float a0 = fminf(fabsf(g0) * 0.70710678f, 4.4f), a1 = fminf(fabsf(g1) * 0.70710678f, 4.4f);
+  float q0 = 1.7291631e-04f, q1 = 1.7291631e-04f;
+  fma2(q0, q1, a0, a1, -3.3274852e-03f);
+  fma2(q0, q1, a0, a1, 2.8219042e-02f);
+  fma2(q0, q1, a0, a1, -1.4366551e-01f);
+  fma2(q0, q1, a0, a1, -9.2350090e-01f);
+  fma2(q0, q1, a0, a1, -1.6263064e+00f);
+  fma2(q0, q1, a0, a1, -7.6538774e-05f);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  const float h0 = 0.5f * e0, h1 = 0.5f * e1;
+  r0 = g0 * (g0 >= 0.f ? 1.f - h0 : h0);
+  r1 = g1 * (g1 >= 0.f ? 1.f - h1 : h1);
+}
+
 // in-place activation of an even-length register array
 template <int N>
 __device__ __forceinline__ void act_apply_n(float* v, int act, float slope) {
@@ -1073,8 +1100,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t w[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float o0 = v[4 * i + 0] * gelu_fast(v[4 * i + 1]) * p.out_scale;
-            const float o1 = v[4 * i + 2] * gelu_fast(v[4 * i + 3]) * p.out_scale;
+            float ge0, ge1;
+            gelu_fast2(v[4 * i + 1], v[4 * i + 3], ge0, ge1);
+            const float o0 = v[4 * i + 0] * ge0 * p.out_scale;
+            const float o1 = v[4 * i + 2] * ge1 * p.out_scale;
             w[i] = (generic && p.out_dtype == CTTA_BF16) ? pack16(o0, o1, 1) : pack_f16_sat(o0, o1);
           }
           if (cw > 1) {
