@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libctta.so")
+LIB_PATH = os.environ.get("CTTA_LIB") or os.path.join(HERE, "libctta.so")   # CTTA_LIB: A/B runs of two builds on one box
 
 F32, F16, BF16 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3, 4

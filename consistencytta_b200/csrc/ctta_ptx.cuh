@@ -68,6 +68,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// The same wait with the bounded spin loop out of line: keeps ~15 instructions per call site out of the instruction
+// stream of kernels with dozens of waits (gemm_tc.cu).  Not for kernels under setmaxnreg (the call needs ABI registers).
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_ool(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
+}
 
 // ---------------------------------------------------------------- TMA loads (tile mode)
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {

@@ -511,7 +511,10 @@ struct GemmBars {
 };
 #define BAR(field, idx) (bar_base + static_cast<uint32_t>(offsetof(GemmBars, field)) + 8u * static_cast<uint32_t>(idx))
 
-template <class Cfg, int NTHREADS = kThreads>
+// DIRECT = 1: the instance for problems whose epilogue cannot go through TMA (direct per-thread global access); it is
+// compiled apart so that the TMA-staged instances do not carry its code (the epilogue warps of the narrow convolutions
+// lost ~9 % of their issue slots to instruction-cache misses in the combined 17 k-instruction kernel).
+template <class Cfg, int NTHREADS = kThreads, int DIRECT = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
@@ -583,7 +586,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const TileCoord tc = decode_tile(p, tile);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           for (int j = 0; j < p.ntaps; ++j) {   // taps are stored group by group
-            mbar_wait(BAR(empty, w_stage), w_phase ^ 1u);
+            mbar_wait_ool(BAR(empty, w_stage), w_phase ^ 1u);
             const uint32_t wfull = BAR(full, w_stage);
             mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(p.w_stage_bytes));
             if (p.w_mcast) {
@@ -614,7 +617,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         for (int sub = 0; sub < p.sub_tiles; ++sub) {
-          mbar_wait(BAR(empty, stage), phase ^ 1u);
+          mbar_wait_ool(BAR(empty, stage), phase ^ 1u);
           const uint32_t full = BAR(full, stage);
           mbar_arrive_expect_tx(full, tx_bytes);
           tma_load_3d(stages_base + static_cast<uint32_t>(stage * p.stage_bytes), &tmap_a, full, 0,
@@ -638,7 +641,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int j = 0; j < p.ntaps; ++j) {
             const int d0 = p.tap_d0[j], d1 = p.tap_d1[j];
             for (int kc = 0; kc < p.k_chunks; ++kc, ++kb) {
-              mbar_wait(BAR(empty, stage), phase ^ 1u);
+              mbar_wait_ool(BAR(empty, stage), phase ^ 1u);
               const uint32_t full = BAR(full, stage);
               mbar_arrive_expect_tx(full, tx_bytes);
               const uint32_t a_dst = stages_base + static_cast<uint32_t>(stage * p.stage_bytes);
@@ -676,18 +679,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = p.acc_single ? 0 : (it & 1);
         const uint32_t acc_phase = p.acc_single ? (it & 1) : ((it >> 1) & 1);
-        mbar_wait(BAR(tmem_empty, acc), acc_phase ^ 1u);
+        mbar_wait_ool(BAR(tmem_empty, acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
         uint32_t started = 0;   // 0 until the first MMA of every sub-tile has been issued
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           const int nkk = (kc == p.k_chunks - 1) ? p.kk_last : kBlockK / 16;
           for (int g = 0; g < p.n_groups; ++g) {
-            mbar_wait(BAR(a_full, a_stage), a_phase);
+            mbar_wait_ool(BAR(a_full, a_stage), a_phase);
             const uint32_t a_base = tiles_base + static_cast<uint32_t>(a_stage * p.a_stage_bytes);
             const int j1 = p.grp_first[g] + p.grp_count[g];
             for (int j = p.grp_first[g]; j < j1; ++j) {
-              mbar_wait(BAR(full, w_stage), w_phase);
+              mbar_wait_ool(BAR(full, w_stage), w_phase);
               tc_fence_after();
               const uint32_t b_lo = umma_desc_lo(w_base + static_cast<uint32_t>(w_stage * p.w_stage_bytes));
               const uint32_t a_lo = umma_desc_lo(a_base) + static_cast<uint32_t>(p.tap_rows[j]) * 8u;
@@ -717,16 +720,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     } else if (leader && p.halo) {
       const uint32_t idesc = umma_idesc(kBlockM, p.block_n, p.is_bf16);
-      mbar_wait(BAR(weights, 0), 0);
+      mbar_wait_ool(BAR(weights, 0), 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = p.acc_single ? 0 : (it & 1);
         const uint32_t acc_phase = p.acc_single ? (it & 1) : ((it >> 1) & 1);
-        mbar_wait(BAR(tmem_empty, acc), acc_phase ^ 1u);
+        mbar_wait_ool(BAR(tmem_empty, acc), acc_phase ^ 1u);
         for (int sub = 0; sub < p.sub_tiles; ++sub) {
-          mbar_wait(BAR(full, stage), phase);
+          mbar_wait_ool(BAR(full, stage), phase);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride + sub * p.block_n);
           const uint32_t a_base = stages_base + static_cast<uint32_t>(stage * p.stage_bytes);
@@ -758,13 +761,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = p.acc_single ? 0 : (it & 1);
         const uint32_t acc_phase = p.acc_single ? (it & 1) : ((it >> 1) & 1);
-        mbar_wait(BAR(tmem_empty, acc), acc_phase ^ 1u);
+        mbar_wait_ool(BAR(tmem_empty, acc), acc_phase ^ 1u);
         tc_fence_after();
         for (int sub = 0; sub < p.sub_tiles; ++sub) {
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride + sub * p.block_n);
         int kc = 0;
         for (int kb = 0; kb < k_iters; ++kb) {
-          mbar_wait(BAR(full, stage), phase);
+          mbar_wait_ool(BAR(full, stage), phase);
           tc_fence_after();
           const uint32_t a_lo = umma_desc_lo(stages_base + static_cast<uint32_t>(stage * p.stage_bytes));
           const uint32_t b_lo = a_lo + (kATileBytes >> 4);
@@ -794,7 +797,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const TileCoord tc = decode_tile(p, tile);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           for (int g = 0; g < p.n_groups; ++g) {
-            mbar_wait(BAR(a_empty, a_stage), a_phase ^ 1u);
+            mbar_wait_ool(BAR(a_empty, a_stage), a_phase ^ 1u);
             const uint32_t afull = BAR(a_full, a_stage);
             mbar_arrive_expect_tx(afull, a_box_bytes * p.a_loads);
             const uint32_t a_dst = tiles_base + static_cast<uint32_t>(a_stage * p.a_stage_bytes);
@@ -842,7 +845,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int col = tc.n0 + ch * io_cols;
           const int srow0 = row0 + sub * kBlockM;
           for (int k = 0; k < p.ring_per_chunk; ++k) {
-            mbar_wait(BAR(ring_empty, slot), phase ^ 1u);
+            mbar_wait_ool(BAR(ring_empty, slot), phase ^ 1u);
             const uint32_t full = BAR(ring_full, slot);
             if (k < p.ring_in) {
               mbar_arrive_expect_tx(full, static_cast<uint32_t>(p.ring_slot_bytes));
@@ -866,7 +869,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
-  } else if (!p.epi_tma) {
+  } else if (DIRECT) {
    if (warp < kEpiWarp0 + 4) {
     // ------------------------------------------------------------------ epilogue warps, direct global access
     // (tiny / unaligned outputs: N <= 16 or row pitch not a multiple of 16 bytes)
@@ -902,7 +905,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const long long ra_row =
           p.rowadd ? (static_cast<long long>(img) * p.rows_per_img + r) / p.rowadd_rows : 0;
 
-      mbar_wait(BAR(tmem_full, acc), acc_phase);
+      mbar_wait_ool(BAR(tmem_full, acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
@@ -935,7 +938,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
    }
-  } else if (warp < kEpiWarp0 + 4 * p.epi_groups) {
+  } else if (!DIRECT && warp < kEpiWarp0 + 4 * p.epi_groups) {
     // ------------------------------------------------------------------ epilogue warps, TMA-staged
     // thread = accumulator row.  Two warps per TMEM lane quarter (group 0 / 1) take alternate 32-column chunks.
     // Per chunk: TMEM -> registers, + bias (smem broadcast) + rowadd, act, + residual / previous out (ring slot,
@@ -1031,7 +1034,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         named_barrier_sync(1, ngrp * 128);
       }
 
-      mbar_wait(BAR(tmem_full, acc), acc_phase);
+      mbar_wait_ool(BAR(tmem_full, acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
       const int last_cc = cc0 < tot_chunks ? ((tot_chunks - 1 - cc0) / ngrp) * ngrp + cc0 : -1;  // last chunk of this group
@@ -1125,7 +1128,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t ring_phase = c_phase;
             for (int k = 0; k < ring_per_chunk; ++k) {
               if (k > 0 && ++slot == p.ring_slots) { slot = 0; ring_phase ^= 1u; }
-              if (hf == 0) mbar_wait(BAR(ring_full, slot), ring_phase);
+              if (hf == 0) mbar_wait_ool(BAR(ring_full, slot), ring_phase);
               const uint32_t sa = ring_base + slot * p.ring_slot_bytes + lr * 128;
               if (k == 0) {
                 slot_addr = sa;
@@ -1926,7 +1929,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
       {N_, 0, 1, 0, 1, 0, N_, gemm_tc_kernel<EpiCfg<N_, 0, 1, 0, 1, 0, N_>>},  // 16-bit out + fp32 residual
       {G_, 0, 0, 0, 1, 0, N_, gemm_tc_kernel<EpiCfg<G_, 0, 0, 0, 1, 0, N_>>},  // GEGLU
   };
-  KernelFn fn = gemm_tc_kernel<EpiGeneric>;
+  KernelFn fn = p.epi_tma ? gemm_tc_kernel<EpiGeneric> : gemm_tc_kernel<EpiGeneric, kThreads, 1>;
   if (p.epi_tma && !p.is_bf16 && d->out_dtype != CTTA_BF16 && getenv("CTTA_GENERIC_EPILOGUE") == nullptr) {
     const int k_act = d->act, k_rowadd = d->rowadd ? 1 : 0, k_ring = p.ring_in;
     const int k_f32 = (d->out && d->out_dtype == CTTA_F32) ? 1 : 0, k_16 = (d->out && d->out_dtype != CTTA_F32) ? 1 : 0;
