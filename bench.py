@@ -307,7 +307,7 @@ def main():
                          "share_of_step": (gemm_ms / ms_step) if gemm_ms else None,
                          "whole_step_tflops": (TOTAL_GFLOP_PER_CLIP if not args.unet_only else GFLOP_PER_CLIP["unet"]) * B / ms_step},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only
             v, sec, threads = cpu_reference_clips_per_s(L, 1, 1)
             line["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
                                     "sample": "2 clips (1 warm-up + 1 timed), batch 1, L=%d, fp32 oracle port, %.1f s/clip"
