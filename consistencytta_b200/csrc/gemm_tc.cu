@@ -18,6 +18,7 @@
 // Reference call sites replaced: see ctta_gemm in include/ctta.h.
 #include <cuda.h>
 #include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -1978,6 +1979,8 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
         q.dynamicSmemBytes = kSmemMaxDynamic;
         CTTA_CUDA(cudaOccupancyMaxActiveClusters(&n_cl, fn, &q));
         max_clusters[reinterpret_cast<const void*>(fn)] = n_cl;
+        if (getenv("CTTA_DEBUG") != nullptr)
+          fprintf(stderr, "ctta_gemm: %d co-resident CTA pairs (persistent grid %d, %d SMs)\n", n_cl, grid, sm_count());
       } else {
         n_cl = itc->second;
       }
