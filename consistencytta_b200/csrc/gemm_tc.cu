@@ -100,7 +100,7 @@ struct GemmKParams {
   int cw, pair, st16_bufs, st16_bytes;   // wide / paired 16-bit epilogue I/O (see the TMA-staged epilogue)
   // stream mode in CTA pairs (cluster of 2): the two CTAs work on neighbouring M tiles of the SAME N tile in lock step;
   // each loads half of every weight chunk and TMA-multicasts it to both, halving the weight bytes an SM pulls from L2
-  int w_mcast, total_tiles_mc;
+  int w_mcast, total_tiles_mc;   // w_mcast = CTAs per cluster (0: independent CTAs, 2 or 4)
   int acc_single;          // 1: one accumulator stage (sub_tiles * block_n * 2 > 512 TMEM columns), else two
   // stream mode (multi-tap convolutions): per (channel chunk, tap group) ONE halo'd activation box is loaded into
   // the A ring and every tap of the group is a row-shifted UMMA view of it; weight chunks stream through their own
@@ -129,10 +129,10 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile)
     // tile = 2 * (pair index q) + half: the CTAs of a pair (consecutive block indices) share q, hence the N tile, and
     // take M tiles 2 * (q / n_tiles_n) + half.  M tiles past the end decode to an out-of-range image: their loads are
     // zero-filled and their stores clipped by the TMA unit, so a pair always runs the same number of tiles.
-    const int half = tile & 1, q = tile >> 1;
+    const int q = tile / p.w_mcast, half = tile - q * p.w_mcast;
     const int qm = q / p.n_tiles_n;
     tc.n0 = (q - qm * p.n_tiles_n) * p.block_n;
-    m_tile = 2 * qm + half;
+    m_tile = p.w_mcast * qm + half;
   } else if (p.n_tiles_n != 1) {   // (one N tile: no division on the per-tile path of the narrow convolutions)
     m_tile = tile / p.n_tiles_n;
     tc.n0 = (tile - m_tile * p.n_tiles_n) * p.block_n;
@@ -535,7 +535,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(BAR(full, s), 1);
-      mbar_init(BAR(empty, s), p.w_mcast ? 2 : 1);   // pair mode: a weight stage is released by both CTAs' MMA warps
+      mbar_init(BAR(empty, s), p.w_mcast ? p.w_mcast : 1);   // cluster mode: a weight stage is released by every CTA's MMA warp
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(tmem_full, s), 1);
@@ -583,6 +583,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t w_phase = 0;
       const uint32_t w_base = tiles_base + static_cast<uint32_t>(p.w_ring_off);
       const uint32_t mc_rank = p.w_mcast ? cluster_ctarank() : 0u;
+      const uint16_t mc_mask = static_cast<uint16_t>((1u << p.w_mcast) - 1u);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -592,9 +593,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(p.w_stage_bytes));
             if (p.w_mcast) {
               // this CTA's half of the chunk (block_n / 2 weight rows) goes to both CTAs of the pair
-              tma_load_2d_mcast(w_base + w_stage * p.w_stage_bytes + mc_rank * (p.w_stage_bytes >> 1), &tmap_b, wfull,
-                                (p.tap_id[j] * p.k_chunks + kc) * kBlockK, tc.n0 + static_cast<int>(mc_rank) * (p.block_n >> 1),
-                                static_cast<uint16_t>(3));
+              tma_load_2d_mcast(w_base + w_stage * p.w_stage_bytes + mc_rank * (p.w_stage_bytes / p.w_mcast), &tmap_b, wfull,
+                                (p.tap_id[j] * p.k_chunks + kc) * kBlockK,
+                                tc.n0 + static_cast<int>(mc_rank) * (p.block_n / p.w_mcast), mc_mask);
             } else {
               tma_load_2d(w_base + w_stage * p.w_stage_bytes, &tmap_b, wfull, (p.tap_id[j] * p.k_chunks + kc) * kBlockK,
                           tc.n0);
@@ -634,6 +635,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       const uint32_t tx_bytes = static_cast<uint32_t>(p.stage_bytes);
       const uint32_t mc_rank = p.w_mcast ? cluster_ctarank() : 0u;
+      const uint16_t mc_mask = static_cast<uint16_t>((1u << p.w_mcast) - 1u);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         for (int sub = 0; sub < p.sub_tiles; ++sub) {
@@ -655,8 +657,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tma_load_4d(a_dst, &tmap_a, full, kc * kBlockK, tc.c1 + d0, tc.c2 + d1, tc.c3);
               }
               if (p.w_mcast)   // CTA pair: this CTA's half of the weight tile goes to both CTAs' stages
-                tma_load_2d_mcast(b_dst + mc_rank * static_cast<uint32_t>(p.block_n * 64), &tmap_b, full, kb * kBlockK,
-                                  tc.n0 + static_cast<int>(mc_rank) * (p.block_n >> 1), static_cast<uint16_t>(3));
+                tma_load_2d_mcast(b_dst + mc_rank * static_cast<uint32_t>(p.block_n * 128 / p.w_mcast), &tmap_b, full, kb * kBlockK,
+                                  tc.n0 + static_cast<int>(mc_rank) * (p.block_n / p.w_mcast), mc_mask);
               else if (p.w_batched) tma_load_3d(b_dst, &tmap_b, full, kb * kBlockK, tc.n0, tc.c2);
               else tma_load_2d(b_dst, &tmap_b, full, kb * kBlockK, tc.n0);
               if (++stage == p.n_stages) {
@@ -703,7 +705,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   umma_chunk_n(nkk, d_tmem + sub * p.block_n, a_lo + sub * (kBlockM * 8), b_lo, idesc, started);
               }
               started = 1;
-              if (p.w_mcast) umma_commit_mcast(BAR(empty, w_stage), static_cast<uint16_t>(3));
+              if (p.w_mcast) umma_commit_mcast(BAR(empty, w_stage), static_cast<uint16_t>((1u << p.w_mcast) - 1u));
               else umma_commit(BAR(empty, w_stage));
               if (++w_stage == p.n_stages) {
                 w_stage = 0;
@@ -776,7 +778,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             umma_chunk<4>(d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
           else
             umma_chunk_n(p.kk_last, d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);  // skip all-zero K slices
-          if (p.w_mcast) umma_commit_mcast(BAR(empty, stage), static_cast<uint16_t>(3));   // both CTAs of the pair
+          if (p.w_mcast) umma_commit_mcast(BAR(empty, stage), static_cast<uint16_t>((1u << p.w_mcast) - 1u));   // every CTA of the cluster
           else umma_commit(BAR(empty, stage));  // frees the smem stage once these MMAs retire
           if (++kc == p.k_chunks) kc = 0;
           if (++stage == p.n_stages) {
@@ -1896,14 +1898,16 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   int grid = sm_count();
   // ---- CTA pairs with multicast weight chunks (see GemmKParams::w_mcast): stream mode, enough tiles for every pair
   const bool mc_generic = !p.stream && !p.halo && p.epi_tma && getenv("CTTA_NO_MCAST_GENERIC") == nullptr;
-  if ((p.stream || mc_generic) && !p.w_batched && block_n >= 128 && block_n % 16 == 0 && p.n_tiles_m >= 2 && (grid % 2) == 0 &&
-      total_tiles >= 2 * grid && getenv("CTTA_NO_MCAST") == nullptr) {
-    p.w_mcast = 1;
-    p.total_tiles_mc = 2 * ((p.n_tiles_m + 1) / 2) * p.n_tiles_n;
+  int cs = getenv("CTTA_MCAST_CS") ? atoi(getenv("CTTA_MCAST_CS")) : 2;   // CTAs per cluster
+  if (cs != 2 && cs != 4) cs = 2;
+  if ((p.stream || mc_generic) && !p.w_batched && block_n >= 128 && block_n % (8 * cs) == 0 && p.n_tiles_m >= cs &&
+      (grid % cs) == 0 && total_tiles >= 2 * grid && getenv("CTTA_NO_MCAST") == nullptr) {
+    p.w_mcast = cs;
+    p.total_tiles_mc = cs * ((p.n_tiles_m + cs - 1) / cs) * p.n_tiles_n;
     total_tiles = p.total_tiles_mc;
     cuuint64_t dims[2] = {(cuuint64_t)d->ntaps * c_pad, (cuuint64_t)d->n};
     cuuint64_t strides[1] = {(cuuint64_t)d->ntaps * c_pad * esz};
-    cuuint32_t box[2] = {kBlockK, (cuuint32_t)(block_n / 2)};
+    cuuint32_t box[2] = {kBlockK, (cuuint32_t)(block_n / cs)};
     int rc = make_tmap(&tmap_b, p.is_bf16, d->wgt, 2, dims, strides, box);
     if (rc) return rc;
   }
@@ -1962,7 +1966,7 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(p.w_mcast);
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -1970,21 +1974,23 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     // co-resident clusters (a GPC with an odd number of free SMs cannot host a last pair): size the persistent grid to them
     {
       static std::mutex mu2;
-      static std::map<const void*, int> max_clusters;
+      static std::map<std::pair<const void*, int>, int> max_clusters;
       std::lock_guard<std::mutex> lock(mu2);
-      auto itc = max_clusters.find(reinterpret_cast<const void*>(fn));
+      const std::pair<const void*, int> ckey(reinterpret_cast<const void*>(fn), p.w_mcast);
+      auto itc = max_clusters.find(ckey);
       int n_cl = 0;
       if (itc == max_clusters.end()) {
         cudaLaunchConfig_t q = cfg;
         q.dynamicSmemBytes = kSmemMaxDynamic;
         CTTA_CUDA(cudaOccupancyMaxActiveClusters(&n_cl, fn, &q));
-        max_clusters[reinterpret_cast<const void*>(fn)] = n_cl;
+        max_clusters[ckey] = n_cl;
         if (getenv("CTTA_DEBUG") != nullptr)
-          fprintf(stderr, "ctta_gemm: %d co-resident CTA pairs (persistent grid %d, %d SMs)\n", n_cl, grid, sm_count());
+          fprintf(stderr, "ctta_gemm: %d co-resident clusters of %d CTAs (persistent grid %d, %d SMs)\n", n_cl, p.w_mcast, grid,
+                  sm_count());
       } else {
         n_cl = itc->second;
       }
-      if (n_cl >= 1 && 2 * n_cl < grid) cfg.gridDim = dim3(static_cast<unsigned>(2 * n_cl));
+      if (n_cl >= 1 && p.w_mcast * n_cl < grid) cfg.gridDim = dim3(static_cast<unsigned>(p.w_mcast * n_cl));
     }
     CTTA_CUDA(cudaLaunchKernelEx(&cfg, fn, tmap_a, tmap_b, tmap_out, tmap_out2, tmap_res, p));
     ::ctta::count_launch();
