@@ -175,6 +175,52 @@ def test_conv1d_lrelu_residual_stream(k, dil, c, t, bsz):
     assert rel(out2, F.leaky_relu(ref, slope)) < 1e-3
 
 
+@pytest.mark.parametrize("kind", ["conv1d_stream", "linear", "conv2d_stream"])
+def test_multicast_cta_pairs_bit_identical(kind, monkeypatch):
+    """The CTA-pair (cluster of 2, TMA-multicast weight chunks) launch computes exactly what independent CTAs compute:
+    same K order, same epilogue.  Shapes with an ODD number of M tiles exercise the padding tile of the last pair
+    (loads zero-filled, stores clipped), with fused GroupNorm moments and a residual in flight."""
+    torch.manual_seed(41)
+    if kind == "conv1d_stream":
+        bsz, t, c = 3, 20484, 256                                  # 161 M tiles per sample x 3 = 483 (odd)
+        x = torch.randn(bsz, t, c, device=DEV).to(DT)
+        res = torch.randn(bsz, t, c, device=DEV).to(DT)
+        pw = ops.pack_conv1d(r16(torch.randn(c, c, 7, device=DEV) / math.sqrt(7 * c)), torch.randn(c, device=DEV), dilation=3)
+
+        def run():
+            out = torch.empty(bsz, t, c, device=DEV, dtype=DT)
+            ops.conv1d(x, pw, residual=res, res_neg_scale=10.0, out2=out, act2=ops.ACT_LRELU, act2_slope=0.1)
+            return out, None
+    elif kind == "linear":
+        m, k, n = 301 * 128 - 40, 320, 512                          # 301 M tiles (odd), ragged last tile, 2 N tiles
+        a = torch.randn(m, k, device=DEV).to(DT)
+        res = torch.randn(m, n, device=DEV)
+        pw = ops.pack_linear(r16(torch.randn(n, k, device=DEV) / math.sqrt(k)), torch.randn(n, device=DEV))
+
+        def run():
+            out = torch.empty(m, n, device=DEV)
+            ops.linear(a, pw, out=out, residual=res)
+            return out, None
+    else:
+        n, h, w, c = 37, 264, 16, 128                              # 33 tiles of 128 pixels per image x 37 = 1221 (odd)
+        x = torch.randn(n, h, w, c, device=DEV).to(DT)
+        pw = ops.pack_conv2d(r16(torch.randn(256, c, 3, 3, device=DEV) / math.sqrt(9 * c)), torch.randn(256, device=DEV))
+
+        def run():
+            out = torch.empty(n, h, w, 256, device=DEV)
+            st = torch.empty(n, 32, 2, device=DEV)
+            ops.conv2d(x, pw, out=out, stats=st, stats_groups=32)
+            return out, st
+    monkeypatch.setenv("CTTA_NO_MCAST", "1")
+    ref, ref_st = run()
+    monkeypatch.delenv("CTTA_NO_MCAST")
+    got, got_st = run()
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+    if ref_st is not None:      # moments are accumulated with fp32 atomics: equal up to summation order
+        assert rel(got_st, ref_st) < 1e-5
+
+
 def test_bmm_nt_batched_weights():
     """Per-image weight matrices (VAE AttnBlock: q.k^T, P.V, W_v.a^T for every sample in one launch)."""
     torch.manual_seed(33)
