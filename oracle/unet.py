@@ -16,7 +16,7 @@ GROUPS = 32
 def timestep_embedding(t, dim=256):
     """diffusers/models/embeddings.py:25-65 with flip_sin_to_cos=True, downscale_freq_shift=0."""
     half = dim // 2
-    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / half
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half
     emb = t.float()[:, None] * torch.exp(exponent)[None, :]
     return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
 
@@ -101,11 +101,11 @@ def unet_forward(sd, sample, timestep, guidance, enc, enc_mask=None):
     enc_bias = None
     if enc_mask is not None:  # :793-795
         enc_bias = ((1 - enc_mask.to(sample.dtype)) * -10000.0).unsqueeze(1)
-    t = torch.as_tensor(timestep).reshape(-1).expand(b)
+    t = torch.as_tensor(timestep).reshape(-1).expand(b).to(sample.device)
     if torch.is_tensor(guidance):
-        g = guidance.reshape(-1).expand(b)
+        g = guidance.reshape(-1).expand(b).to(sample.device)
     else:
-        g = torch.tensor([float(guidance)], dtype=torch.float64).expand(b)
+        g = torch.tensor([float(guidance)], dtype=torch.float64).expand(b).to(sample.device)
     t_emb = mlp_embedding(sd, "time_embedding", timestep_embedding(t).to(sample.dtype))  # :803-808
     g_emb = mlp_embedding(sd, "guidance_embedding", fourier_embedding(g, sd["guidance_proj.weight"]).to(sample.dtype))
     emb = t_emb + g_emb  # :816

@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Stock-PyTorch bar on the SAME B200 (SURVEY.md 8d "GPU reference baseline"): the fp32 oracle restatement of the
+reference's modules (the reference itself is a Python tree that does not exist on the GPU box) run in eager mode on
+cuda:0 — fp32 with TF32 matmuls/convs (torch's default for convs), and under bf16 autocast as `inference.py` can be run —
+next to this repository's engine at the same batch.  Not collected by pytest (no `test_` prefix); lives under tests/
+because only tests/, smoke() and bench.py's CPU leg may execute oracle/.
+
+    python tests/torch_eager_gpu_baseline.py --batch 8 --iters 3
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from consistencytta_b200 import SingleStepEngine, build_random_init_models, weights  # noqa: E402
+from oracle import hifigan, pipeline  # noqa: E402
+
+
+def timed(fn, iters):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--text-len", type=int, default=32)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    usd = {k: v.to(dev) for k, v in weights.make_unet_state_dict(0).items()}
+    vsd = {k: v.to(dev) for k, v in weights.make_vae_state_dict(1).items()}
+    noise, enc, mask = (t.to(dev) for t in weights.synthetic_inputs(a.batch, a.text_len))
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    out = {"batch": a.batch, "text_len": a.text_len, "gpu": torch.cuda.get_device_name(0), "torch": torch.__version__}
+
+    def eager():
+        with torch.no_grad():
+            lat, mel, wav = pipeline.generate(usd, vsd, weights.SCALE_FACTOR, noise, enc, mask, 4.0)
+            return lat, mel, wav
+
+    def eager_bf16():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return pipeline.generate(usd, vsd, weights.SCALE_FACTOR, noise, enc, mask, 4.0)
+
+    ms = timed(eager, a.iters)
+    out["torch_eager_fp32_tf32"] = {"ms_per_step": ms, "clips_per_s": a.batch / ms * 1e3}
+    ref_lat, ref_mel, ref_wav = eager()
+    ms = timed(eager_bf16, a.iters)
+    out["torch_eager_bf16_autocast"] = {"ms_per_step": ms, "clips_per_s": a.batch / ms * 1e3}
+    del usd, vsd
+    torch.cuda.empty_cache()
+    unet, vae = build_random_init_models(dev)
+    eng = SingleStepEngine(unet, vae, use_graphs=True)
+    res = eng.run(noise, enc, mask, 4.0)
+    ms = timed(lambda: eng.run(noise, enc, mask, 4.0), max(a.iters, 5))
+    out["consistencytta_b200"] = {"ms_per_step": ms, "clips_per_s": a.batch / ms * 1e3}
+    rel = lambda x, y: ((x.double() - y.double()).norm() / y.double().norm()).item()
+    out["parity_vs_torch_eager"] = {"latent_rel_l2": rel(res["latent"], ref_lat), "mel_rel_l2": rel(res["mel"], ref_mel)}
+    out["speedup_vs_fp32_tf32"] = out["consistencytta_b200"]["clips_per_s"] / out["torch_eager_fp32_tf32"]["clips_per_s"]
+    out["speedup_vs_bf16_autocast"] = out["consistencytta_b200"]["clips_per_s"] / out["torch_eager_bf16_autocast"]["clips_per_s"]
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
