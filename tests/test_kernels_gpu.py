@@ -221,6 +221,42 @@ def test_multicast_cta_pairs_bit_identical(kind, monkeypatch):
         assert rel(got_st, ref_st) < 1e-5
 
 
+def test_bf16_operands_generic_epilogue():
+    """The C-ABI also takes bf16 operands (generic epilogue instance): fp32-output linear, the HiFi-GAN residual stream
+    with 128-byte epilogue rows (C = 64), the paired-row N = 32 layout, and a GEGLU linear with bf16 output."""
+    torch.manual_seed(43)
+    bf = torch.bfloat16
+    rb = lambda t: t.to(bf).float()
+    # linear, fp32 out + residual
+    m, k, n = 1000, 256, 320
+    a, w, b = rb(torch.randn(m, k, device=DEV)), rb(torch.randn(n, k, device=DEV) / math.sqrt(k)), torch.randn(n, device=DEV)
+    res = torch.randn(m, n, device=DEV)
+    out = torch.empty(m, n, device=DEV)
+    ops.linear(a.to(bf), ops.pack_linear(w, b, dtype=bf), out=out, residual=res)
+    assert rel(out, a @ w.t() + b + res) < 2e-5
+    # GEGLU, bf16 out
+    d = 256
+    w2, b2 = rb(torch.randn(2 * d, k, device=DEV) / math.sqrt(k)), torch.randn(2 * d, device=DEV)
+    wi = torch.stack([w2[:d], w2[d:]], dim=1).reshape(2 * d, k)
+    bi = torch.stack([b2[:d], b2[d:]], dim=1).reshape(2 * d)
+    o16 = torch.empty(m, d, device=DEV, dtype=bf)
+    ops.linear(a.to(bf), ops.pack_linear(wi, bi, dtype=bf), out=o16, act=ops.ACT_GEGLU)
+    h = a @ w2.t() + b2
+    assert rel(o16, h[:, :d] * F.gelu(h[:, d:])) < 6e-3
+    # conv1d residual stream (lrelu'ed 16-bit residual -> lrelu'ed 16-bit operand): C = 64 (wide rows), C = 32 (paired rows)
+    for c, t in ((64, 3000), (32, 3000)):
+        slope = 0.1
+        lx = F.leaky_relu(torch.randn(2, t, c, device=DEV), slope).to(bf)
+        x = rb(torch.randn(2, t, c, device=DEV))
+        wt, bc = rb(torch.randn(c, c, 7, device=DEV) / math.sqrt(7 * c)), torch.randn(c, device=DEV)
+        out2 = torch.empty(2, t, c, device=DEV, dtype=bf)
+        ops.conv1d(x.to(bf), ops.pack_conv1d(wt, bc, dilation=1, dtype=bf), residual=lx, res_neg_scale=1.0 / slope, out2=out2,
+                   act2=ops.ACT_LRELU, act2_slope=slope)
+        lxf = lx.float()
+        ref = F.conv1d(x.permute(0, 2, 1), wt, bc, padding=3).permute(0, 2, 1) + torch.where(lxf < 0, lxf / slope, lxf)
+        assert rel(out2, F.leaky_relu(ref, slope)) < 6e-3
+
+
 def test_bmm_nt_batched_weights():
     """Per-image weight matrices (VAE AttnBlock: q.k^T, P.V, W_v.a^T for every sample in one launch)."""
     torch.manual_seed(33)
