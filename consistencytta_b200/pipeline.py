@@ -24,6 +24,17 @@ LATENT_SHAPE = (8, 256, 16)
 WAVE_SAMPLES = 163872  # 1024 mel frames through ups 5*4*2*2*2 with odd (k - s) in the first stage
 
 
+def slice_request_rows(t, lo, hi, b, cf):
+    """Rows [lo, hi) of a per-request tensor of a b-clip request.  Scalars and broadcast (1-row) tensors pass through;
+    with post-CFG (`cf`) text tensors hold 2b rows laid out [unconditional ; conditional] (consistencytta.py:171,
+    audio_consistency_model.py:441) and the slice keeps that layout."""
+    if t is None or not torch.is_tensor(t) or t.dim() == 0 or t.shape[0] == 1:
+        return t
+    if cf and t.shape[0] == 2 * b:
+        return torch.cat([t[lo:hi], t[b + lo:b + hi]])
+    return t[lo:hi]
+
+
 class SingleStepEngine:
     """One bucket of static buffers + one CUDA graph per (batch, text length, sigma, post-CFG, stage) key.
 
@@ -163,11 +174,7 @@ class SingleStepEngine:
             out["wav"] = torch.empty(b, WAVE_SAMPLES, device=dev, dtype=torch.float32)
 
         def rows(t, lo, hi):
-            if t is None or not torch.is_tensor(t) or t.dim() == 0 or t.shape[0] == 1:
-                return t
-            if cf and t.shape[0] == 2 * b:
-                return torch.cat([t[lo:hi], t[b + lo:b + hi]])
-            return t[lo:hi]
+            return slice_request_rows(t, lo, hi, b, cf)
 
         for lo in range(0, b, self.max_batch):
             hi = min(lo + self.max_batch, b)

@@ -173,3 +173,21 @@ def test_bench_reference_arm_line_and_nonzero_rank_exit():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
+
+
+def test_micro_batch_row_slicing_keeps_cfg_layout():
+    """Host logic of SingleStepEngine._run_micro_batches: per-request tensors are sliced per micro-batch; with post-CFG
+    the text tensors are [unconditional ; conditional] (2b rows) and every slice must keep that layout."""
+    from consistencytta_b200.pipeline import slice_request_rows
+    b = 5
+    enc = torch.arange(2 * b).float().view(2 * b, 1, 1).expand(2 * b, 3, 4)
+    s = slice_request_rows(enc, 2, 4, b, True)
+    assert s.shape == (4, 3, 4) and s[:, 0, 0].tolist() == [2.0, 3.0, 7.0, 8.0]
+    assert slice_request_rows(enc[:b], 4, 5, b, False)[:, 0, 0].tolist() == [4.0]
+    g = torch.tensor([1.0, 2.0, 3.0, 4.0, 5.0])
+    assert slice_request_rows(g, 0, 2, b, True).tolist() == [1.0, 2.0]          # per-clip guidance: b rows even with CFG
+    assert slice_request_rows(torch.tensor([3.0]), 2, 4, b, True).tolist() == [3.0]   # broadcast value
+    assert slice_request_rows(4.0, 0, 2, b, False) == 4.0 and slice_request_rows(None, 0, 2, b, False) is None
+    # the slices of all micro-batches cover every row exactly once, in order
+    got = torch.cat([slice_request_rows(enc, lo, min(lo + 2, b), b, True)[: min(lo + 2, b) - lo] for lo in range(0, b, 2)])
+    assert got[:, 0, 0].tolist() == [0.0, 1.0, 2.0, 3.0, 4.0]
