@@ -258,13 +258,14 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int i = 0; i < 128; ++i)
           if (i >= valid) s[i] = -INFINITY;
       }
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+      // row maximum with three-input max (FMNMX3): 64 instructions for 128 values, four independent chains
+      float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]), mx2 = fmaxf(s[4], s[5]), mx3 = fmaxf(s[6], s[7]);
 #pragma unroll
-      for (int i = 4; i < 128; i += 4) {
-        mx0 = fmaxf(mx0, s[i]);
-        mx1 = fmaxf(mx1, s[i + 1]);
-        mx2 = fmaxf(mx2, s[i + 2]);
-        mx3 = fmaxf(mx3, s[i + 3]);
+      for (int i = 8; i < 128; i += 8) {
+        mx0 = max3(mx0, s[i], s[i + 1]);
+        mx1 = max3(mx1, s[i + 2], s[i + 3]);
+        mx2 = max3(mx2, s[i + 4], s[i + 5]);
+        mx3 = max3(mx3, s[i + 6], s[i + 7]);
       }
       const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
       bool waited_pv = false;
@@ -296,16 +297,18 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ATC_STAMP(3);
       const float mc = m_used * c;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      const float nmc = -mc;
+      // exponent arguments and row sums on packed fp32 pairs (FFMA2 / FADD2): per value 1/2 + 1 (MUFU) + 1/2 issue slots
 #pragma unroll
       for (int i = 0; i < 128; i += 4) {
-        s[i] = fast_exp2(fmaf(s[i], c, -mc));
-        s[i + 1] = fast_exp2(fmaf(s[i + 1], c, -mc));
-        s[i + 2] = fast_exp2(fmaf(s[i + 2], c, -mc));
-        s[i + 3] = fast_exp2(fmaf(s[i + 3], c, -mc));
-        l0 += s[i];
-        l1 += s[i + 1];
-        l2 += s[i + 2];
-        l3 += s[i + 3];
+        fma2_ss(s[i], s[i + 1], c, nmc);
+        fma2_ss(s[i + 2], s[i + 3], c, nmc);
+        s[i] = fast_exp2(s[i]);
+        s[i + 1] = fast_exp2(s[i + 1]);
+        s[i + 2] = fast_exp2(s[i + 2]);
+        s[i + 3] = fast_exp2(s[i + 3]);
+        add2_acc(l0, l1, s[i], s[i + 1]);
+        add2_acc(l2, l3, s[i + 2], s[i + 3]);
       }
       l_sum += (l0 + l1) + (l2 + l3);
       ATC_STAMP(4);

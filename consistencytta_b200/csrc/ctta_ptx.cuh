@@ -20,6 +20,29 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
   return r;
 }
 
+// sm_100 packed / three-input fp32 arithmetic (FFMA2, FADD2, FMNMX3): same IEEE results as the scalar forms, half the
+// issue slots.
+__device__ __forceinline__ void fma2_ss(float& x0, float& x1, float a, float b) {   // x = x * a + b on both halves
+  uint64_t x, av, bv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x) : "l"(x), "l"(av), "l"(bv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+}
+__device__ __forceinline__ void add2_acc(float& a0, float& a1, float b0, float b1) {   // a += b on both halves
+  uint64_t a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // One lane of a CONVERGED warp.  Unlike `lane == 0`, ptxas knows exactly one thread is active behind this predicate,
 // so warp-uniform instructions (UTCHMMA, UTMALDG, UTMASTG, UTCBAR) are issued straight instead of inside an
 // ELECT / BRA.U.ANY serialisation loop (about 12 extra SASS instructions per tcgen05.mma otherwise).
