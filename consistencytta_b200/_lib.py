@@ -46,7 +46,7 @@ SIGNATURES = {
     "ctta_attention_debug": (C.c_int, [C.POINTER(C.c_longlong)]),
     "ctta_softmax_rows": (C.c_int, [_P, _I32, _I32, _I64, _F, _P, _I32, _I64, _P]),
     "ctta_im2col_s2": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P]),
-    "ctta_nchw_to_nhwc": (C.c_int, [_P, _I32, _I32, _I32, _P, _I32, _I32, _F, _P]),
+    "ctta_nchw_to_nhwc": (C.c_int, [_P, _I32, _I32, _I32, _P, _I32, _I32, _F, _P, _P]),
     "ctta_nhwc_to_nchw": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P]),
     "ctta_time_features": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P]),
     "ctta_small_linear": (C.c_int, [_P, _I32, _I32, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),

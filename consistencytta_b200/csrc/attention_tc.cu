@@ -412,12 +412,8 @@ int attention_tc_launch(const void* q, const void* k, const void* v, void* o, in
     p.dbg = dbg_buf;
     g_attn_dbg = dbg_buf;
   }
-  static bool configured = false;
-  if (!configured) {
-    CTTA_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(flash_attn_tc_kernel),
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal + 1024));
-    configured = true;
-  }
+  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(flash_attn_tc_kernel), kSmemTotal + 1024);
+  if (rc) return rc;
   dim3 grid((lq + 2 * kTile - 1) / (2 * kTile), heads, batch);
   flash_attn_tc_kernel<<<grid, kThreads, kSmemTotal + 1024, stream>>>(tq, tk, tv, p);
   CTTA_LAUNCH_CHECK();

@@ -8,7 +8,10 @@ namespace ctta {
 int set_error(int code, const char* fmt, ...);
 extern std::atomic<long long> g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
-int sm_count();
+constexpr int kMaxDevices = 64;
+int current_device();                                    // cudaGetDevice (0 on error)
+int sm_count();                                          // SM count of the CURRENT device (cached per device)
+int ensure_dynamic_smem(const void* fn, int bytes);      // cudaFuncAttributeMaxDynamicSharedMemorySize once per (device, fn)
 }  // namespace ctta
 
 #define CTTA_REQUIRE(cond, ...)                                                  \

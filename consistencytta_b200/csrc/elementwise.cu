@@ -37,8 +37,9 @@ __device__ __forceinline__ unsigned short cvt16e(float v, int dtype) {
   return __half_as_ushort(__float2half_rn(v));
 }
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n_img, int c, int hw, void* __restrict__ y,
-                                    int y_dtype, int y_ld, float scale) {
+                                    int y_dtype, int y_ld, float scale, const float* __restrict__ scale_dev) {
   const long long total = static_cast<long long>(n_img) * hw * c;
+  if (scale_dev != nullptr) scale *= __ldg(scale_dev);
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int ch = static_cast<int>(idx % c);
@@ -234,11 +235,11 @@ extern "C" int ctta_im2col_s2(const void* x, int32_t n_img, int32_t h, int32_t w
 }
 
 extern "C" int ctta_nchw_to_nhwc(const float* x, int32_t n_img, int32_t c, int32_t hw, void* y, int32_t y_dtype,
-                                 int32_t y_ld, float scale, void* stream_v) {
+                                 int32_t y_ld, float scale, const float* scale_dev, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   CTTA_REQUIRE(x && y && n_img > 0 && c > 0 && hw > 0 && y_ld >= c, "nchw_to_nhwc: bad arguments");
   const long long total = static_cast<long long>(n_img) * hw * c;
-  nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, n_img, c, hw, y, y_dtype, y_ld, scale);
+  nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, n_img, c, hw, y, y_dtype, y_ld, scale, scale_dev);
   CTTA_LAUNCH_CHECK();
   return 0;
 }

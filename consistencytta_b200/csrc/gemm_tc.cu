@@ -1949,14 +1949,8 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
   }
   const int n_threads = kThreads;
   {
-    static std::mutex mu;
-    static std::set<const void*> configured;
-    std::lock_guard<std::mutex> lock(mu);
-    if (!configured.count(reinterpret_cast<const void*>(fn))) {
-      CTTA_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kSmemMaxDynamic));
-      configured.insert(reinterpret_cast<const void*>(fn));
-    }
+    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(fn), kSmemMaxDynamic);
+    if (rc) return rc;
   }
   if (p.w_mcast) {
     cudaLaunchConfig_t cfg{};
@@ -1974,9 +1968,9 @@ extern "C" int ctta_gemm(const ctta_gemm_desc* d, void* stream_v) {
     // co-resident clusters (a GPC with an odd number of free SMs cannot host a last pair): size the persistent grid to them
     {
       static std::mutex mu2;
-      static std::map<std::pair<const void*, int>, int> max_clusters;
+      static std::map<std::pair<const void*, int>, int> max_clusters;   // key: (fn, device * 16 + cluster size)
       std::lock_guard<std::mutex> lock(mu2);
-      const std::pair<const void*, int> ckey(reinterpret_cast<const void*>(fn), p.w_mcast);
+      const std::pair<const void*, int> ckey(reinterpret_cast<const void*>(fn), current_device() * 16 + p.w_mcast);
       auto itc = max_clusters.find(ckey);
       int n_cl = 0;
       if (itc == max_clusters.end()) {

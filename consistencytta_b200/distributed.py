@@ -1,8 +1,9 @@
 """Multi-GPU plumbing: prompts shard by batch across ranks, one process per GPU, no collective on the hot path.
 
 The reference has no multi-GPU inference at all (single process, `CUDA_VISIBLE_DEVICES=$which_gpu`,
-inference.sh:13); clips are independent end to end, so the only communication is gathering the int16 waveforms
-(320 KB / clip) for output and, optionally, a 2-float all-reduce that reproduces the reference's *batch-global*
+inference.sh:13); clips are independent end to end, so the only communication is collecting the int16 waveforms
+(320 KB / clip) on rank 0 for output (`WaveformGatherer`: a gather to ONE rank on a side stream, overlapped with the next
+step's compute; `gather_waveforms` is the all-ranks variant) and, optionally, a 2-float all-reduce that reproduces the reference's *batch-global*
 waveform centring (hifigan/utilities.py:84-85) across shards.  torch.distributed (NCCL on GPUs, gloo in the CPU
 tests) is plumbing only.
 """
@@ -70,3 +71,106 @@ def gather_waveforms(local, n_global=None, sizes=None):
     if n_global is not None:
         assert out.shape[0] == n_global
     return out
+
+
+class WaveformGatherer:
+    """Collects every rank's int16 clips [B_local, T] on rank 0 — the only rank that writes files (inference.py:221-222)
+    — without stalling the compute stream.
+
+    `submit(local)` copies the clips into one of two staging buffers on the caller's stream (the engine's output buffer is
+    overwritten by the next replay) and issues `dist.gather(dst=0)` on a side stream; the caller's stream never waits
+    for the transfer, only — two submits later — for the staging buffer to be free again.  `result()` makes the caller's
+    stream wait for the last transfer and returns rank 0's [n_global, T] tensor (None elsewhere).  Rows are padded to
+    the largest shard so unequal shards work; per-rank waveform centring stays the default (each rank is an independent
+    `vocoder_infer` batch, hifigan/utilities.py:84-86), `global_minmax` being the opt-in for single-process equality."""
+
+    def __init__(self, sizes, row_shape, device, dtype=torch.int16, rank=None, world=None):
+        self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank() if dist.is_initialized() else 0)
+        self.sizes = list(sizes)
+        assert len(self.sizes) == self.world
+        self.m = max(self.sizes)
+        self.row_shape = tuple(row_shape)
+        self.dtype = dtype
+        self.device = torch.device(device)
+        row_bytes = torch.empty((), dtype=dtype).element_size()
+        for d in self.row_shape:
+            row_bytes *= d
+        self.row_bytes = row_bytes
+        self.cuda = self.device.type == "cuda"
+        # neither NCCL nor gloo transports int16: ship the raw bytes
+        self.stage = [torch.zeros(self.m, row_bytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.recv = None
+        if self.rank == 0 and self.world > 1:
+            # one contiguous [world, m, row] buffer per slot: with equal shards the result is a VIEW of it (no torch.cat)
+            self.recv = [torch.empty(self.world, self.m, row_bytes, dtype=torch.uint8, device=self.device)
+                         for _ in range(2)]
+        self.side = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.done = [None, None]
+        self.k = 0
+        self.last = None
+
+    def submit(self, local):
+        assert local.shape[0] == self.sizes[self.rank] and tuple(local.shape[1:]) == self.row_shape
+        slot = self.k & 1
+        self.k += 1
+        if self.world == 1:
+            self.last = (slot, local.contiguous().view(torch.uint8).reshape(local.shape[0], self.row_bytes))
+            return
+        # typed view of the staging slot: a strided `local` (e.g. clips[:, :160000]) is copied exactly once
+        stage = self.stage[slot].view(self.dtype).reshape((self.m,) + self.row_shape)
+        if self.cuda:
+            cur = torch.cuda.current_stream(self.device)
+            if self.done[slot] is not None:
+                cur.wait_event(self.done[slot])          # the transfer that last used this staging slot has finished
+            stage[: local.shape[0]].copy_(local, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ready)
+                dist.gather(self.stage[slot], list(self.recv[slot].unbind(0)) if self.rank == 0 else None, dst=0)
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+            self.done[slot] = ev
+        else:
+            stage[: local.shape[0]].copy_(local)
+            dist.gather(self.stage[slot], list(self.recv[slot].unbind(0)) if self.rank == 0 else None, dst=0)
+        self.last = (slot, None)
+
+    def to_host(self, host_out):
+        """Rank 0, equal shards: copies the LAST gathered batch into pinned host memory on the side stream (overlapped with
+        whatever the caller's stream does next) — the files are written from there (inference.py:221-222)."""
+        if self.rank != 0 or self.last is None:
+            return
+        slot, raw = self.last
+        if self.world == 1:
+            host_out.view(torch.uint8).reshape(-1, self.row_bytes).copy_(raw, non_blocking=True)
+            return
+        assert all(n == self.m for n in self.sizes), "to_host needs equal shards"
+        src = self.recv[slot].view(self.world * self.m, self.row_bytes)
+        dst = host_out.view(torch.uint8).reshape(self.world * self.m, self.row_bytes)
+        if self.cuda:
+            with torch.cuda.stream(self.side):
+                dst.copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+            self.done[slot] = ev
+        else:
+            dst.copy_(src)
+
+    def result(self):
+        """Rank 0: [n_global, *row_shape] of the LAST submit (ordered after it on the current stream); others: None."""
+        if self.last is None:
+            return None
+        slot, raw = self.last
+        if self.world == 1:
+            return raw.view(self.dtype).reshape((-1,) + self.row_shape)
+        if self.cuda and self.done[slot] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.done[slot])
+        if self.rank != 0:
+            return None
+        if all(n == self.m for n in self.sizes):
+            out = self.recv[slot].view(self.world * self.m, self.row_bytes)
+        else:
+            out = torch.cat([b[:n] for b, n in zip(self.recv[slot].unbind(0), self.sizes)])
+        return out.view(self.dtype).reshape((-1,) + self.row_shape)

@@ -22,6 +22,10 @@ _DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 def _require_cuda(t):
     if not t.is_cuda:
         raise _lib.CttaError("consistencytta_b200 ops need CUDA tensors (no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the current device's stream; a tensor of another GPU would be dereferenced on the wrong one
+        raise _lib.CttaError("tensor lives on %s but the current CUDA device is %d: wrap the call in "
+                             "torch.cuda.device(tensor.device)" % (t.device, torch.cuda.current_device()))
 
 
 def _stream():
@@ -422,8 +426,9 @@ def im2col_s2(x):
     return out
 
 
-def nchw_to_nhwc(x, dtype=torch.float32, scale=1.0, c_pad=None, out=None):
-    """fp32 NCHW -> channels-last [N, H, W, c_pad] (zero padded channels), multiplied by `scale`."""
+def nchw_to_nhwc(x, dtype=torch.float32, scale=1.0, c_pad=None, out=None, scale_dev=None):
+    """fp32 NCHW -> channels-last [N, H, W, c_pad] (zero padded channels), multiplied by `scale` (and by the device
+    scalar `scale_dev`, fp32 [1], when given)."""
     _require_cuda(x)
     x = x.contiguous().float()
     n, c, h, w = x.shape
@@ -431,7 +436,7 @@ def nchw_to_nhwc(x, dtype=torch.float32, scale=1.0, c_pad=None, out=None):
     if out is None:
         out = (torch.zeros if cp != c else torch.empty)(n, h, w, cp, device=x.device, dtype=dtype)
     dtype = out.dtype
-    check(lib().ctta_nchw_to_nhwc(_ptr(x), n, c, h * w, _ptr(out), _DT[dtype], cp, scale, _stream()))
+    check(lib().ctta_nchw_to_nhwc(_ptr(x), n, c, h * w, _ptr(out), _DT[dtype], cp, scale, _ptr(scale_dev), _stream()))
     return out
 
 

@@ -23,6 +23,18 @@ from .ops import ACT_GEGLU, ACT_NONE, ACT_SILU
 HEAD_PAD = 64
 
 
+def prefix_mask_lengths(mask):
+    """bool / 0-1 mask [B, L] with True only on a prefix of each row -> int32 [B] counts; anything else raises
+    (the attention kernels take a key COUNT per row; an interior hole would be silently mis-applied)."""
+    m = mask.to(torch.bool)
+    if m.dim() != 2:
+        raise ValueError("encoder_attention_mask must be [batch, text_len], got %s" % (tuple(m.shape),))
+    if m.shape[1] > 1 and bool((~m[:, :-1] & m[:, 1:]).any()):
+        raise ValueError("encoder_attention_mask must be a prefix mask (trailing padding only): a True after a False "
+                         "cannot be expressed as a key count")
+    return m.sum(dim=1).to(torch.int32)
+
+
 class FrozenConfig(dict):
     """dict with attribute access, like diffusers' FrozenDict (configuration_utils.py)."""
 
@@ -322,12 +334,31 @@ class UNet2DConditionGuidedModel(PackedModule):
         return v.expand(b).contiguous()
 
     def kv_lengths(self, encoder_attention_mask, b, n_text, dev):
+        """encoder_attention_mask (bool [B, L]) -> per-row key count.  The kernels SKIP keys >= kv_len instead of adding
+        the reference's -10000 bias (attention_processor.py:374-397), which is the same thing for the trailing-padding
+        masks a tokenizer produces; a mask with an interior False cannot be expressed as a count and is refused."""
         if encoder_attention_mask is None:
             return None
-        return encoder_attention_mask.to(dev).sum(dim=1).to(torch.int32).contiguous()
+        return prefix_mask_lengths(encoder_attention_mask).to(dev).contiguous()
 
-    def forward_nhwc(self, sample, timestep, guidance, enc, enc_mask=None, kv_len=None, sample_is_nhwc=False):
-        """Channels-last core: returns fp32 [B, 256, 16, 8].  `kv_len` int32 [B] may be given instead of a mask."""
+    def project_text(self, enc, out=None):
+        """K and V of every cross-attention site for prompt embeddings `enc` [B, L, 1024] (attention_processor.py:
+        1117-1118): ONE GEMM against the 32 stacked to_k / to_v matrices -> 16-bit [B, L, 32 * heads * 64].  The result
+        depends on the prompt only, so callers cache it across num_samples / multi-step queries (`enc_kv=`)."""
+        pk = self.packed()
+        dev = self.device
+        b, n_text, _ = enc.shape
+        enc16 = ops.groupnorm_apply(enc.to(dev).float().contiguous().view(b, n_text, 1, -1), 1, None, None, None,
+                                    act=ACT_NONE)
+        if out is None:
+            out = torch.empty(b, n_text, pk["kv_all"].n, device=dev, dtype=ops.OPERAND_DTYPE)
+        ops.linear(enc16.view(b * n_text, -1), pk["kv_all"], out=out.view(b * n_text, -1))
+        return out
+
+    def forward_nhwc(self, sample, timestep, guidance, enc, enc_mask=None, kv_len=None, sample_is_nhwc=False,
+                     enc_kv=None):
+        """Channels-last core: returns fp32 [B, 256, 16, 8].  `kv_len` int32 [B] may be given instead of a mask;
+        `enc_kv` (from `project_text`) replaces `enc` when the prompt's K/V were already projected."""
         pk = self.packed()
         dev = self.device
         f16 = ops.OPERAND_DTYPE
@@ -339,7 +370,7 @@ class UNet2DConditionGuidedModel(PackedModule):
         else:
             b = sample.shape[0]
             x0 = ops.nchw_to_nhwc(sample.to(dev).float(), dtype=f16)
-        n_text = enc.shape[1]
+        n_text = enc_kv.shape[1] if enc_kv is not None else enc.shape[1]
         if kv_len is None:
             # trailing padding only (T5 tokenizer); masked keys == truncated keys
             kv_len = self.kv_lengths(enc_mask, b, n_text, dev)
@@ -358,10 +389,8 @@ class UNet2DConditionGuidedModel(PackedModule):
         ops.linear(emb16.view(b, -1), pk["temb_all"], out=temb_all)
 
         # 2. text K/V for every cross-attention site (attention_processor.py:1117-1118), one GEMM
-        enc16 = ops.groupnorm_apply(enc.to(dev).float().contiguous().view(b, n_text, 1, -1), 1, None, None, None,
-                                    act=ACT_NONE)
-        enc_kv = torch.empty(b, n_text, pk["kv_all"].n, device=dev, dtype=f16)
-        ops.linear(enc16.view(b * n_text, -1), pk["kv_all"], out=enc_kv.view(b * n_text, -1))
+        if enc_kv is None:
+            enc_kv = self.project_text(enc)
 
         # 3. down path.  `st` carries the GroupNorm moments of x whenever the kernel that produced x could emit them
         _, hh, ww, _ = x0.shape

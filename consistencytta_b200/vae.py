@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from . import ops, weights
-from .module_base import PackedModule, _Node, register_tree
+from .module_base import PackedModule, _Node, next_pack_version, register_tree
 from .ops import ACT_LRELU, ACT_NONE, ACT_SILU, ACT_TANH
 
 GROUPS = 32
@@ -171,9 +171,11 @@ class Decoder(PackedModule):
         wv = pk[p + ".v"]
         # all samples at once (batched GEMMs: image i multiplies its own K-major operand):
         #   V^T[i] = W_v . a[i]^T,   S[i] = q[i] . k[i]^T (fp32),   P = softmax(S / sqrt(c)),   o[i] = P[i] . V[i] + b_v
-        wv_rep = pk.get((p, "v_rep"))   # W_v replicated per sample: the A operand of the batched V^T GEMM
-        if wv_rep is None or wv_rep.shape[0] != b:
-            wv_rep = pk[(p, "v_rep")] = wv.w.unsqueeze(0).expand(b, c, c).contiguous()
+        # W_v replicated per sample: the A operand of the batched V^T GEMM.  One entry PER BATCH SIZE, never replaced:
+        # captured CUDA graphs hold the raw pointer, and a freed entry would be recycled by the caching allocator
+        wv_rep = pk.get((p, "v_rep", b))
+        if wv_rep is None:
+            wv_rep = pk[(p, "v_rep", b)] = wv.w.unsqueeze(0).expand(b, c, c).contiguous()
         vt = torch.empty(b, c, n, device=dev, dtype=f16)
         ops.bmm_nt(wv_rep, a, out=vt)
         s = torch.empty(b, n, n, device=dev, dtype=torch.float32)
@@ -252,21 +254,83 @@ class AutoencoderKL(nn.Module):
         self.image_key = image_key
         self.time_shuffle = time_shuffle
         self.scale_factor = scale_factor
-        self._pq = None
+        self._pq = {}
+        self._pq_version = next_pack_version()
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module._drop_post_quant())
 
     @property
     def device(self):
         return next(self.parameters()).device
 
     def load_state_dict(self, state_dict, strict=True, **kw):
-        """Accepts the reference's 398-key VAE state_dict; encode-side tensors are dropped (out of scope)."""
-        sd = {k: v for k, v in state_dict.items() if not k.startswith(("encoder.", "quant_conv."))}
-        self._pq = None
+        """Accepts the reference's 398-key VAE state_dict; encode-side tensors are dropped (out of scope).  A state_dict
+        that carries `ema_decoder.*` / `ema_post_quant_conv.*` (a VAE saved after fine-tuning with
+        models/audio_consistency_model_ftvae.py:52-65) creates the EMA modules before loading."""
+        sd = {k: v for k, v in state_dict.items() if not k.startswith(("encoder.", "quant_conv.", "loss."))}
+        if self.ema_decoder is None and any(k.startswith(("ema_decoder.", "ema_post_quant_conv.")) for k in sd):
+            self.enable_ema_modules()
+        self._drop_post_quant()
         return super().load_state_dict(sd, strict=strict, **kw)
 
+    def enable_ema_modules(self):
+        """EMA copies of the decoder and post_quant_conv (audio_consistency_model_ftvae.py:52-65), selected by
+        `decode_first_stage(..., use_ema=True)` (autoencoder.py:91-97)."""
+        from copy import deepcopy
+        dev = self.device
+        self.ema_decoder = deepcopy(self.decoder)
+        self.ema_decoder._invalidate()
+        self.ema_decoder.requires_grad_(False).eval()
+        self.ema_post_quant_conv = deepcopy(self.post_quant_conv)
+        self.ema_post_quant_conv.requires_grad_(False)
+        self._drop_post_quant()
+        return self.to(dev)
+
+    @classmethod
+    def from_vae_state_dict_file(cls, path_or_obj, **kw):
+        """`consistencytta_clapft_ckpt/vae_state_dict.pt` = {"state_dict", "scale_factor"} (consistencytta.py:32-44)."""
+        raw = torch.load(path_or_obj, map_location="cpu") if isinstance(path_or_obj, (str, bytes)) or hasattr(
+            path_or_obj, "read") else path_or_obj
+        sf = raw["scale_factor"]
+        vae = cls(scale_factor=float(sf.item() if torch.is_tensor(sf) else sf), **kw)
+        vae.load_state_dict(raw["state_dict"])
+        vae.eval().requires_grad_(False)
+        return vae
+
+    @classmethod
+    def from_audioldm_checkpoint(cls, path_or_obj, **kw):
+        """An AudioLDM checkpoint {"state_dict": {"first_stage_model.*", "scale_factor", ...}}: keeps the first-stage
+        tensors with the 18-character prefix removed and reads the latent scale (tools/build_pretrained.py:9-22)."""
+        ckpt = torch.load(path_or_obj, map_location="cpu") if isinstance(path_or_obj, (str, bytes)) or hasattr(
+            path_or_obj, "read") else path_or_obj
+        sd = ckpt["state_dict"]
+        sf = sd["scale_factor"]
+        vae_sd = {k[len("first_stage_model."):]: v for k, v in sd.items() if "first_stage_model." in k}
+        vae = cls(scale_factor=float(sf.item() if torch.is_tensor(sf) else sf), **kw)
+        vae.load_state_dict(vae_sd)
+        vae.eval().requires_grad_(False)
+        return vae
+
+    def _drop_post_quant(self):
+        self._pq = {}
+        self._pq_version = next_pack_version()
+
     def _apply(self, fn, *a, **k):
-        self._pq = None
+        self._drop_post_quant()
         return super()._apply(fn, *a, **k)
+
+    @property
+    def pack_version(self):
+        """Changes whenever any packed operand of the decode path may have been rebuilt (see PackedModule)."""
+        mods = [self.decoder, self.vocoder] + ([self.ema_decoder] if self.ema_decoder is not None else [])
+        return (self._pq_version,) + tuple(m.pack_version for m in mods)
+
+    def to_prepacked(self, device):
+        """`.to(device)` with the decoder / vocoder operands packed on the host first (PackedModule.to_prepacked)."""
+        self.to(device)
+        for m in (self.decoder, self.vocoder, self.ema_decoder):
+            if m is not None:
+                m.to_prepacked(device)
+        return self
 
     def encode(self, x):
         raise NotImplementedError("the VAE encode side is training/evaluation only (SURVEY.md 8a V1)")
@@ -278,10 +342,10 @@ class AutoencoderKL(nn.Module):
         mod = self.post_quant_conv
         if use_ema and self.ema_post_quant_conv is not None:
             mod = self.ema_post_quant_conv
-        key = (id(mod), float(z_scale))
-        if self._pq is None or self._pq[0] != key:
-            self._pq = (key, ops.pack_conv2d(mod.weight.detach().float() * float(z_scale), mod.bias.detach()))
-        return self._pq[1]
+        key = ("ema" if mod is self.ema_post_quant_conv else "raw", float(z_scale), str(mod.weight.device))
+        if key not in self._pq:   # one entry per key, kept alive: captured graphs hold the pointer
+            self._pq[key] = ops.pack_conv2d(mod.weight.detach().float() * float(z_scale), mod.bias.detach())
+        return self._pq[key]
 
     def decode_nhwc(self, z_nhwc, use_ema=False, z_scale=1.0, mel16=None):
         """z_nhwc: fp32 channels-last latent [B, 256, 16, 8] -> fp32 [B, 1024, 64, 1] (== NCHW [B,1,1024,64]).

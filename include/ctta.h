@@ -184,9 +184,12 @@ int ctta_softmax_rows(const float* x, int32_t rows, int32_t cols, int64_t ld, fl
 /* Gather for the three stride-2 3x3 convs (resnet.py:206): x[n, h, w, c] 16-bit -> a[n*(h/2)*(w/2), 9*c]. */
 int ctta_im2col_s2(const void* x, int32_t n_img, int32_t h, int32_t w, int32_t c, void* a, void* stream);
 
-/* NCHW fp32 <-> channels-last conversions at the module boundary. dst 16-bit or fp32. */
+/* NCHW fp32 <-> channels-last conversions at the module boundary. dst 16-bit or fp32.  y = x * scale * (*scale_dev):
+ * `scale_dev` (device float, may be NULL = 1) carries the scheduler prologue `z_N = noise * init_noise_sigma` +
+ * `scale_model_input` (easy_inference/consistencytta.py:160,173; scheduling_heun_discrete.py:151-172) as DATA, so one
+ * captured CUDA graph serves every sigma of the multi-step sampler. */
 int ctta_nchw_to_nhwc(const float* x, int32_t n_img, int32_t c, int32_t hw, void* y, int32_t y_dtype, int32_t y_ld,
-                      float scale, void* stream);
+                      float scale, const float* scale_dev, void* stream);
 int ctta_nhwc_to_nchw(const float* x, int32_t n_img, int32_t c, int32_t hw, int32_t ld, float* y, void* stream);
 
 /* Timestep + guidance embedding front end (embeddings.py:25-65,222-249; unet_2d_condition_guided.py:803-816):

@@ -35,7 +35,34 @@ def import_reference():
     from diffusers import HeunDiscreteScheduler, UNet2DConditionGuidedModel
     from audioldm.variational_autoencoder import AutoencoderKL
     from audioldm.utils import default_audioldm_config
+    import_reference.DDIM = import_reference_ddim()
     return UNet2DConditionGuidedModel, HeunDiscreteScheduler, AutoencoderKL, default_audioldm_config
+
+
+def import_reference_ddim():
+    """The reference's DDIMScheduler lives only in the FULL tree (/root/reference/diffusers/schedulers/scheduling_ddim.py),
+    whose package __init__ does not import under this image's transformers / huggingface_hub.  Its source file is
+    executed unmodified, from where it lies, inside a stand-in package whose three relative imports (configuration_utils,
+    utils.{BaseOutput, randn_tensor}, scheduling_utils) resolve to the same helpers of the trimmed easy_inference copy."""
+    import importlib.util
+    import types
+    from diffusers.utils import configuration_utils, outputs, scheduling_utils, torch_utils
+    pkg = types.ModuleType("refddim")
+    pkg.__path__ = []
+    sub = types.ModuleType("refddim.schedulers")
+    sub.__path__ = []
+    utils = types.ModuleType("refddim.utils")
+    utils.BaseOutput = outputs.BaseOutput
+    utils.randn_tensor = torch_utils.randn_tensor
+    sys.modules.update({"refddim": pkg, "refddim.schedulers": sub, "refddim.utils": utils,
+                        "refddim.configuration_utils": configuration_utils,
+                        "refddim.schedulers.scheduling_utils": scheduling_utils})
+    path = os.path.join(os.path.dirname(REF.rstrip("/")), "diffusers", "schedulers", "scheduling_ddim.py")
+    spec = importlib.util.spec_from_file_location("refddim.schedulers.scheduling_ddim", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    return mod.DDIMScheduler
 
 
 def rel(a, b):
@@ -121,6 +148,50 @@ def main():
         wav_c = vae.vocoder(mel_c.squeeze(1).permute(0, 2, 1)).squeeze(1).float()
         out["c_mel"], out["c_wav"] = mel_c, wav_c
         report["oracle_vs_reference"]["wav_c"] = rel(o_hifigan.decode_to_waveform(vae_sd, mel_c, True), wav_c)
+
+        # ---------------- case D: multi-step consistency sampling with the REFERENCE scheduler objects
+        # (easy_inference/consistencytta.py:159-197 verbatim, torch.randn_like replaced by fixed step noises): 4 steps,
+        # B = 1, L = 8 -> queries at t = 999, 666, 333, 0
+        noise, enc, mask = weights.synthetic_inputs(1, 8, seed=77)
+        g = torch.Generator().manual_seed(78)
+        step_noises = [torch.randn(1, 8, 256, 16, generator=g) for _ in range(3)]
+        sched.set_timesteps(18)
+        z_N = noise * sched.init_noise_sigma
+
+        def calc_zhat_0(z_n, t):
+            z_n_input = sched.scale_model_input(z_n, t)
+            return unet(z_n_input, t, guidance=3.0, encoder_hidden_states=enc, encoder_attention_mask=mask).sample
+
+        zhat_0 = calc_zhat_0(z_N, sched.timesteps[0])
+        sched.set_timesteps(4)
+        ts_d = [float(t) for t in sched.timesteps[1::2]]
+        for i, t in enumerate(sched.timesteps[1::2]):
+            zhat_n = sched.add_noise(zhat_0, step_noises[i], t)
+            zhat_0 = calc_zhat_0(zhat_n, t)
+        out["d_latent"] = zhat_0
+        report["case_d_timesteps"] = ts_d
+        o_lat_d = o_pipe.generate_latent_multistep(unet_sd, noise, step_noises, enc, mask, 3.0, 4)
+        report["oracle_vs_reference"]["latent_d_multistep4"] = rel(o_lat_d, zhat_0)
+
+        # ---------------- case E: the non-EDM variant (inference.py:159-162 without --use_edm): reference DDIMScheduler,
+        # models/audio_consistency_model.py:486-507 with use_edm False (stride 1), 2 steps -> queries at t = 935, 0
+        ddim = import_reference.DDIM(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012,
+                                     beta_schedule="scaled_linear", prediction_type="v_prediction")
+        ddim.set_timesteps(18)
+        z_N = noise * ddim.init_noise_sigma
+        t0_e = ddim.timesteps[0]
+        zhat_0 = unet(ddim.scale_model_input(z_N, t0_e), t0_e, guidance=3.0, encoder_hidden_states=enc,
+                      encoder_attention_mask=mask).sample
+        ddim.set_timesteps(2)
+        ts_e = [int(t0_e)] + [int(t) for t in ddim.timesteps[1::1]]
+        for i, t in enumerate(ddim.timesteps[1::1]):
+            zhat_n = ddim.add_noise(zhat_0, step_noises[i], t)
+            zhat_0 = unet(ddim.scale_model_input(zhat_n, t), t, guidance=3.0, encoder_hidden_states=enc,
+                          encoder_attention_mask=mask).sample
+        out["e_latent"] = zhat_0
+        report["case_e_timesteps"] = ts_e
+        o_lat_e = o_pipe.generate_latent_multistep_ddim(unet_sd, noise, step_noises, enc, mask, 3.0, 2)
+        report["oracle_vs_reference"]["latent_e_ddim2"] = rel(o_lat_e, zhat_0)
 
     print(json.dumps(report, indent=1))
     for k, v in report["oracle_vs_reference"].items():

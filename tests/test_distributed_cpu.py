@@ -37,7 +37,14 @@ def _worker(rank, world, port, n_global, q):
         gmm = D.global_minmax(mm)
         i16 = (wav * 100).to(torch.int16)
         full = D.gather_waveforms(i16, n_global)
-        q.put((rank, mine, noise.tolist(), gmm.tolist(), full.tolist()))
+        # gather to rank 0 only (two submits: both staging slots), unequal shards included
+        sizes = [D.shard_bounds(n_global, world, r)[1] - D.shard_bounds(n_global, world, r)[0] for r in range(world)]
+        gat = D.WaveformGatherer(sizes, (5,), "cpu")
+        gat.submit(i16 + 1)
+        gat.submit(i16)
+        root = gat.result()
+        assert (root is None) == (rank != 0)
+        q.put((rank, mine, noise.tolist(), gmm.tolist(), full.tolist(), root.tolist() if root is not None else None))
     finally:
         dist.destroy_process_group()
 
@@ -63,6 +70,8 @@ def test_shard_gather_gloo(world, n_global):
     for r in res:
         assert torch.allclose(torch.tensor(r[3]), torch.stack([ref_wav.min(), ref_wav.max()]))
         assert torch.equal(torch.tensor(r[4], dtype=torch.int16).reshape(n_global, 5), (ref_wav * 100).to(torch.int16))
+    assert torch.equal(torch.tensor(res[0][5], dtype=torch.int16).reshape(n_global, 5), (ref_wav * 100).to(torch.int16))
+    assert all(r[5] is None for r in res[1:])
 
 
 def test_shard_bounds_balanced():

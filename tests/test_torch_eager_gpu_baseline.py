@@ -2,10 +2,12 @@
 """Stock-PyTorch bar on the SAME B200 (SURVEY.md 8d "GPU reference baseline"): the fp32 oracle restatement of the
 reference's modules (the reference itself is a Python tree that does not exist on the GPU box) run in eager mode on
 cuda:0 — fp32 with TF32 matmuls/convs (torch's default for convs), and under bf16 autocast as `inference.py` can be run —
-next to this repository's engine at the same batch.  Not collected by pytest (no `test_` prefix); lives under tests/
-because only tests/, smoke() and bench.py's CPU leg may execute oracle/.
+next to this repository's engine at the same batch.  Lives under tests/ because only tests/, smoke() and bench.py's
+CPU leg may execute oracle/.  Collected by pytest (`-m gpu`) at batch 8: the parity leg uses the STRICT fp32 eager run
+(TF32 off) as a second, GPU-side oracle — latent, mel AND waveform SNR — and the speed leg asserts the engine beats
+stock bf16-autocast eager.  As a script it prints the JSON record kept under profiles/:
 
-    python tests/torch_eager_gpu_baseline.py --batch 8 --iters 3
+    python tests/test_torch_eager_gpu_baseline.py --batch 64 --iters 3
 """
 import argparse
 import json
@@ -32,12 +34,8 @@ def timed(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--iters", type=int, default=3)
-    ap.add_argument("--text-len", type=int, default=32)
-    a = ap.parse_args()
+def run(batch=8, iters=3, text_len=32):
+    a = argparse.Namespace(batch=batch, iters=iters, text_len=text_len)
     dev = torch.device("cuda", 0)
     usd = {k: v.to(dev) for k, v in weights.make_unet_state_dict(0).items()}
     vsd = {k: v.to(dev) for k, v in weights.make_vae_state_dict(1).items()}
@@ -58,7 +56,11 @@ def main():
 
     ms = timed(eager, a.iters)
     out["torch_eager_fp32_tf32"] = {"ms_per_step": ms, "clips_per_s": a.batch / ms * 1e3}
-    ref_lat, ref_mel, ref_wav = eager()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ref_lat, ref_mel, ref_wav = eager()      # strict fp32: the parity reference
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
     ms = timed(eager_bf16, a.iters)
     out["torch_eager_bf16_autocast"] = {"ms_per_step": ms, "clips_per_s": a.batch / ms * 1e3}
     del usd, vsd
@@ -69,10 +71,41 @@ def main():
     ms = timed(lambda: eng.run(noise, enc, mask, 4.0), max(a.iters, 5))
     out["consistencytta_b200"] = {"ms_per_step": ms, "clips_per_s": a.batch / ms * 1e3}
     rel = lambda x, y: ((x.double() - y.double()).norm() / y.double().norm()).item()
-    out["parity_vs_torch_eager"] = {"latent_rel_l2": rel(res["latent"], ref_lat), "mel_rel_l2": rel(res["mel"], ref_mel)}
+    d = res["wav"].double() - ref_wav.double()
+    snr = float(10 * torch.log10(ref_wav.double().pow(2).sum() / d.pow(2).sum()))
+    out["parity_vs_torch_eager_fp32"] = {"latent_rel_l2": rel(res["latent"], ref_lat), "mel_rel_l2": rel(res["mel"], ref_mel),
+                                         "wav_snr_db": snr}
     out["speedup_vs_fp32_tf32"] = out["consistencytta_b200"]["clips_per_s"] / out["torch_eager_fp32_tf32"]["clips_per_s"]
     out["speedup_vs_bf16_autocast"] = out["consistencytta_b200"]["clips_per_s"] / out["torch_eager_bf16_autocast"]["clips_per_s"]
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--text-len", type=int, default=32)
+    a = ap.parse_args()
+    print(json.dumps(run(a.batch, a.iters, a.text_len)))
+
+
+try:
+    import pytest
+except ImportError:  # script use without pytest
+    pytest = None
+
+if pytest is not None:
+    @pytest.mark.gpu
+    def test_engine_matches_and_beats_stock_torch_eager_on_gpu():
+        out = run(batch=8, iters=2)
+        print(json.dumps(out))
+        par = out["parity_vs_torch_eager_fp32"]
+        assert par["latent_rel_l2"] <= 1e-2 and par["mel_rel_l2"] <= 1e-2 and par["wav_snr_db"] >= 35.0
+        assert out["speedup_vs_bf16_autocast"] > 1.5 and out["speedup_vs_fp32_tf32"] > 2.0
+        d = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(d):
+            with open(os.path.join(d, "torch_eager_gpu_baseline_b8.json"), "w") as f:
+                json.dump(out, f)
 
 
 if __name__ == "__main__":
