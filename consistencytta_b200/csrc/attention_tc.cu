@@ -2,17 +2,32 @@
 //
 // One CTA = one (batch, head) and 256 query rows = two independent 128-row tiles that share every K/V tile.
 // 12 warps: warps 0..3 / 4..7 = softmax warp groups of query tile 0 / 1 (thread == query row, so the row max / row sum
-// need no shuffles; setmaxnreg gives them 224 registers), warp 8 = TMA loader (Q once, K/V through a 3-stage ring),
+// need no shuffles; setmaxnreg gives them 216 registers), warp 8 = TMA loader (Q once, K/V through a 3-stage ring),
 // warp 9 = single-thread tcgen05.mma issuer.  The two softmax groups share the SM's MUFU pipes, so group 1 starts half
 // an iteration late: one group's exponentials then overlap the other's TMEM loads / packing / stores.  Per key tile of 128:
 //     S_t   = Q_t K^T            UMMA 128x128x64, fp32 in TMEM (S_t: 128 columns)
 //     P_t   = exp2(c S_t - c m)  softmax warps: tcgen05.ld -> registers -> packed 16-bit P back into TMEM (tcgen05.st)
 //     O_t  += P_t V              UMMA 128x64x128 with A = P_t from tensor memory; V is the MN-major B operand exactly
 //                                as TMA lands it ([keys, d])
-// The issuer runs QK^T of key tile j+1 as soon as the softmax warps have pulled S(j) into registers, so the tensor
-// core works under the exponentials.  The running max is updated lazily: O_t (in TMEM) is only rescaled when some row
-// of the warp saw its max grow by more than 2^8, which keeps P <= 256 and the result exact (the same stale max is
-// used for the row sum).  Keys >= kv_len[b] get -inf, i.e. the reference's additive -10000 mask bias.
+// The issuer runs QK^T of key tile j+1 as soon as the softmax warps are done with S(j), so the tensor core works under
+// the packing / storing of P(j) and the softmax of the other query tile.
+//
+// At head dim 64 the softmax, not the tensor pipe, is the bound: 16 ex2/clk/SM = 1024 MUFU cycles per 128x128 tile against
+// 736 tensor cycles, and each softmax warp's own serial chain on top (two warps per scheduler).  Three measures (r2):
+//  * OPTIMISTIC softmax: a tile's probabilities are evaluated against the running max of the EARLIER tiles without
+//    looking for the tile's own row max; the tile's row sum (needed anyway) is the overflow detector (sum <= 2^15 => every
+//    P <= 2^15 fits the 16-bit P).  Only when a row fails it, or on the first tile, the scores are re-read from tensor
+//    memory, the true max is taken, O_t / l are rescaled and the tile is re-evaluated.  Exact: softmax is shift
+//    invariant, and the same stale max is used for the row sum.  Saves 64 FMNMX3 + a dependent reduction per tile.
+//  * 3 of every 8 pairs of exponentials are evaluated on the FMA pipe instead of MUFU (Cody-Waite split + degree-3 minimax
+//    polynomial, 7.5e-5 relative error, below the 4.9e-4 rounding of the 16-bit P).
+//  * instruction diet: the phase timestamps and the 16-bit type are compile-time (a run-time dtype flag issued both
+//    converts, each timestamp ~10 instructions of predicate arithmetic per tile), barrier addresses are pinned in
+//    registers, hot waits are a 2-instruction spin.
+// Measured on the 64 x 5 x 4096^2 site: 2.09 -> 1.64 ms (profiles/r2_attn_*.txt).  Rejected by measurement: a four-stream
+// split-KV layout (16 softmax warps, P through shared memory): S 2x128 + O 4x64 fills tensor memory, P then has to go
+// through shared memory and the kernel becomes shared-memory / issue bound (2.07 ms).
+// Keys >= kv_len[b] get -inf, i.e. the reference's additive -10000 mask bias.
 //
 // Reference call site: F.scaled_dot_product_attention, diffusers/models/attention_processor.py:1127-1129.
 #include <cuda.h>
@@ -39,7 +54,8 @@ constexpr int kSmemP = kSmemKV + kStages * 2 * kTileBytes;   // per query tile: 
 constexpr int kSmemTotal = kSmemP;                           // 128 KiB (P lives in tensor memory)
 constexpr int kTmemCols = 512;
 constexpr int kColS = 0, kColO = 256, kColP = 384;   // S_t at 128 t, O_t at 256 + 64 t, P_t (16-bit pairs) at 384 + 64 t
-constexpr float kLazyThreshold = 8.f;        // log2 units
+constexpr int kDefaultPoly = 3;               // 3 of 8 pairs (37.5 %) of the exponentials on the FMA pipe (measured best of 0 / 2 / 3 / 4)
+constexpr float kSumLimit = 32768.f;         // optimistic softmax: a tile whose probabilities sum to <= 2^15 cannot overflow the 16-bit P
 
 struct Params {
   int lq, lk, heads;
@@ -50,11 +66,38 @@ struct Params {
   int is_bf16;
   long long* dbg;   // optional phase timestamps of CTA 0 / softmax warp 0 (tools/attn_phases.py), else NULL
 };
+// compiled in only for the DBG instantiation: each stamp costs ~10 instructions of predicate arithmetic per key tile
 #define ATC_STAMP(slot)                                                            \
   do {                                                                             \
-    if (p.dbg != nullptr && blockIdx.x + blockIdx.y + blockIdx.z == 0 && warp == 0 && lane == 0 && j >= 8 && j < 16) \
+    if (DBG && blockIdx.x + blockIdx.y + blockIdx.z == 0 && warp == 0 && lane == 0 && j >= 8 && j < 16) \
       p.dbg[(j - 8) * 8 + (slot)] = clock64();                                     \
   } while (0)
+
+// Hot-loop wait: a plain try_wait spin (2 instructions per round); the wall-clock bound that turns a protocol bug into a
+// trap instead of a hang is only consulted every 4096 failed rounds.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {   // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFFu) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (t0 == 0) t0 = t1;
+      else if (t1 - t0 > 20000000000ULL) __trap();
+    }
+  }
+}
 
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
   asm volatile(
@@ -97,12 +140,55 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ uint32_t pack_p(float a, float b, int is_bf16) {
+template <int BF16>
+__device__ __forceinline__ uint32_t pack_p(float a, float b) {   // compile-time type: a runtime flag issues both converts
   uint32_t r;
-  if (is_bf16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  if (BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+
+// ---- packed fp32 pairs (FFMA2 / FADD2)
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// 2^x for two values on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x) (magic-number add), f in [-0.5, 0.5],
+// 2^f by a degree-3 minimax polynomial (7.5e-5 max relative error), 2^n by adding n to the exponent field.
+// x is clamped to >= -125 so that the exponent add never leaves the normal range (-inf / masked keys -> 2^-125 ~ 0).
+__device__ __forceinline__ void exp2_poly2(float& x0, float& x1) {
+  const float kMagic = 12582912.f;   // 1.5 * 2^23
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  const uint64_t x = pk2(x0, x1);
+  const uint64_t t = add2(x, pk2(kMagic, kMagic));
+  const uint64_t n = add2(t, pk2(-kMagic, -kMagic));
+  const uint64_t f = fma2(n, pk2(-1.f, -1.f), x);
+  uint64_t r = fma2(f, pk2(0.05517132207751274f, 0.05517132207751274f), pk2(0.24261054396629333f, 0.24261054396629333f));
+  r = fma2(r, f, pk2(0.6932609677314758f, 0.6932609677314758f));
+  r = fma2(r, f, pk2(0.9999281167984009f, 0.9999281167984009f));
+  float t0, t1, r0, r1;
+  upk2(t, t0, t1);
+  upk2(r, r0, r1);
+  x0 = __int_as_float(__float_as_int(r0) + (__float_as_int(t0) << 23));
+  x1 = __int_as_float(__float_as_int(r1) + (__float_as_int(t1) << 23));
+}
+
+// POLY: of every 8 pairs of exponentials, POLY pairs are evaluated on the FMA pipe instead of MUFU (0 .. 4 -> 0 .. 50 %)
+template <int POLY, int BF16, int DBG>
 
 __global__ void __launch_bounds__(kThreads, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -177,8 +263,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one_sync()) {
-      const uint32_t idesc_qk = umma_idesc(kTile, kTile, p.is_bf16);                 // 128 x 128, A and B K-major
-      const uint32_t idesc_pv = umma_idesc(kTile, kD, p.is_bf16) | (1u << 16);       // 128 x 64, B (= V) MN-major
+      const uint32_t idesc_qk = umma_idesc(kTile, kTile, BF16);                 // 128 x 128, A and B K-major
+      const uint32_t idesc_pv = umma_idesc(kTile, kD, BF16) | (1u << 16);       // 128 x 64, B (= V) MN-major
       mbar_wait(smem_u32(&bar_q_full), 0);
       mbar_wait(smem_u32(&bar_kv_full[0]), 0);
       tc_fence_after();
@@ -236,87 +322,107 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t o_addr = tmem_base + lane_addr + kColO + t * kD;
     const uint32_t p_addr = tmem_base + lane_addr + kColP + t * 64;
     const float c = p.scale_log2;
+    // barrier addresses pinned in registers (ptxas otherwise re-derives the shared-window address at each use)
+    const uint32_t a_s_full = pin_u32(smem_u32(&bar_s_full[t])), a_s_free = pin_u32(smem_u32(&bar_s_free[t]));
+    const uint32_t a_p_full = pin_u32(smem_u32(&bar_p_full[t])), a_pv_done = pin_u32(smem_u32(&bar_pv_done[t]));
     float m_used = -INFINITY, l_sum = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t par = static_cast<uint32_t>(j & 1);
       ATC_STAMP(0);
-      mbar_wait(smem_u32(&bar_s_full[t]), par);
+      mbar_wait_lean(a_s_full, par);
       tc_fence_after();
       ATC_STAMP(1);
       uint32_t u[128];
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) tmem_ld_x32(s_addr + ch * 32, u + ch * 32);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_s_free[t]));
-      ATC_STAMP(2);
       float* s = reinterpret_cast<float*>(u);
       const int valid = kvl - j * kTile;            // keys of this tile below kv_len
-      if (valid < kTile) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= valid) s[i] = -INFINITY;
-      }
-      // row maximum with three-input max (FMNMX3): 64 instructions for 128 values, four independent chains
-      float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]), mx2 = fmaxf(s[4], s[5]), mx3 = fmaxf(s[6], s[7]);
-#pragma unroll
-      for (int i = 8; i < 128; i += 8) {
-        mx0 = max3(mx0, s[i], s[i + 1]);
-        mx1 = max3(mx1, s[i + 2], s[i + 3]);
-        mx2 = max3(mx2, s[i + 4], s[i + 5]);
-        mx3 = max3(mx3, s[i + 6], s[i + 7]);
-      }
-      const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
       bool waited_pv = false;
-      if (j == 0) {
-        m_used = m_new;
-      } else {
-        const bool need = (m_new - m_used) * c > kLazyThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          // rescale O_t (and the row sum) to the new max; needs PV(j-1) to have landed in TMEM
-          mbar_wait(smem_u32(&bar_pv_done[t]), par ^ 1u);
-          waited_pv = true;
-          tc_fence_after();
-          const float alpha = fast_exp2((m_used - m_new) * c);
-          m_used = m_new;
-          l_sum *= alpha;
+      float tile_sum = 0.f;
+      // OPTIMISTIC softmax: the probabilities of a tile are first evaluated against the running max m_used of the earlier
+      // tiles WITHOUT looking for the tile's own row max (64 FMNMX3 + a dependent reduction per tile).  The row sum of
+      // the tile, which is needed anyway, is the overflow detector: sum <= 2^15 implies every P <= 2^15, exactly
+      // representable in the 16-bit P (and a NaN / inf sum fails the test).  Only when some row of the warp fails it — a
+      // key beat the stale max by more than ~2^15, or this is the first tile — the scores are read from tensor memory
+      // again (S_t is released to the next Q K^T only after the check), the true row max is taken, O_t and the row sum are
+      // rescaled and the tile is re-evaluated.  Any m works for softmax as long as nothing overflows, so this is exact.
 #pragma unroll 1
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t o[32];
-            tmem_ld_x32(o_addr + hh * 32, o);
-            tmem_ld_wait();
+      for (int attempt = 0; attempt < 2; ++attempt) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x32(o_addr + hh * 32, o);
-          }
-          tmem_st_wait();
+        for (int ch = 0; ch < 4; ++ch) tmem_ld_x32(s_addr + ch * 32, u + ch * 32);
+        tmem_ld_wait();
+        if (valid < kTile) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= valid) s[i] = -INFINITY;
         }
-      }
-      if (j == 0 && t == 1) mbar_wait(smem_u32(&bar_stagger), 0);   // start half an iteration behind group 0
-      ATC_STAMP(3);
-      const float mc = m_used * c;
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      const float nmc = -mc;
-      // exponent arguments and row sums on packed fp32 pairs (FFMA2 / FADD2): per value 1/2 + 1 (MUFU) + 1/2 issue slots
+        if (attempt == 1 || j == 0) {
+          // true row maximum with three-input max (FMNMX3), eight independent chains
+          float mx[8];
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
-        fma2_ss(s[i], s[i + 1], c, nmc);
-        fma2_ss(s[i + 2], s[i + 3], c, nmc);
-        s[i] = fast_exp2(s[i]);
-        s[i + 1] = fast_exp2(s[i + 1]);
-        s[i + 2] = fast_exp2(s[i + 2]);
-        s[i + 3] = fast_exp2(s[i + 3]);
-        add2_acc(l0, l1, s[i], s[i + 1]);
-        add2_acc(l2, l3, s[i + 2], s[i + 3]);
+          for (int k = 0; k < 8; ++k) mx[k] = fmaxf(s[2 * k], s[2 * k + 1]);
+#pragma unroll
+          for (int i = 16; i < 128; i += 16) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mx[k] = max3(mx[k], s[i + 2 * k], s[i + 2 * k + 1]);
+          }
+          const float m_new = fmaxf(max3(max3(mx[0], mx[1], mx[2]), max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])), m_used);
+          if (j > 0) {
+            // rescale O_t (and the row sum) to the new max; needs PV(j-1) to have landed in TMEM
+            mbar_wait_lean(a_pv_done, par ^ 1u);
+            waited_pv = true;
+            tc_fence_after();
+            const float alpha = fast_exp2((m_used - m_new) * c);
+            l_sum *= alpha;
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t o[32];
+              tmem_ld_x32(o_addr + hh * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x32(o_addr + hh * 32, o);
+            }
+            tmem_st_wait();
+          }
+          m_used = m_new;
+        }
+        if (attempt == 0 && j == 0 && t == 1) mbar_wait(smem_u32(&bar_stagger), 0);   // start half an iteration behind group 0
+        ATC_STAMP(3);
+        const float nmc = -m_used * c;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        // exponent arguments and row sums on packed fp32 pairs (FFMA2 / FADD2); of every 8 pairs, POLY go to the FMA pipe
+#pragma unroll
+        for (int i = 0; i < 128; i += 16) {
+#pragma unroll
+          for (int pr = 0; pr < 8; ++pr) fma2_ss(s[i + 2 * pr], s[i + 2 * pr + 1], c, nmc);
+#pragma unroll
+          for (int pr = 0; pr < 8; ++pr) {
+            if (pr >= 8 - POLY) {
+              exp2_poly2(s[i + 2 * pr], s[i + 2 * pr + 1]);
+            } else {
+              s[i + 2 * pr] = fast_exp2(s[i + 2 * pr]);
+              s[i + 2 * pr + 1] = fast_exp2(s[i + 2 * pr + 1]);
+            }
+          }
+#pragma unroll
+          for (int pr = 0; pr < 8; pr += 2) {
+            add2_acc(l0, l1, s[i + 2 * pr], s[i + 2 * pr + 1]);
+            add2_acc(l2, l3, s[i + 2 * pr + 2], s[i + 2 * pr + 3]);
+          }
+        }
+        tile_sum = (l0 + l1) + (l2 + l3);
+        const bool bad = !(tile_sum <= kSumLimit);
+        if (attempt == 1 || j == 0 || !__any_sync(0xffffffffu, bad)) break;
       }
-      l_sum += (l0 + l1) + (l2 + l3);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_s_free);         // S_t may be overwritten by the next Q K^T
+      l_sum += tile_sum;
       ATC_STAMP(4);
       if (j == 0 && t == 0) {
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_stagger));
       }
-      if (j > 0 && !waited_pv) mbar_wait(smem_u32(&bar_pv_done[t]), par ^ 1u);   // PV(j-1) no longer reads P_t
+      if (j > 0 && !waited_pv) mbar_wait_lean(a_pv_done, par ^ 1u);   // PV(j-1) no longer reads P_t
       ATC_STAMP(5);
       {
         // P_t -> tensor memory as packed 16-bit pairs (the A operand of the P.V UMMA): row = lane, 64 columns
@@ -324,14 +430,14 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) w[i] = pack_p(s[64 * hh + 2 * i], s[64 * hh + 2 * i + 1], p.is_bf16);
+          for (int i = 0; i < 32; ++i) w[i] = pack_p<BF16>(s[64 * hh + 2 * i], s[64 * hh + 2 * i + 1]);
           tmem_st_x32(p_addr + hh * 32, w);
         }
         tmem_st_wait();
       }
       tc_fence_before();     // orders the P store and the O rescale (tcgen05.st) before the arrive
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_p_full[t]));
+      if (lane == 0) mbar_arrive(a_p_full);
       ATC_STAMP(6);
     }
     // ---- epilogue: O_t / l -> 16-bit, this thread's row
@@ -348,10 +454,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         uint4 w;
-        w.x = pack_p(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv, p.is_bf16);
-        w.y = pack_p(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv, p.is_bf16);
-        w.z = pack_p(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv, p.is_bf16);
-        w.w = pack_p(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv, p.is_bf16);
+        w.x = pack_p<BF16>(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+        w.y = pack_p<BF16>(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+        w.z = pack_p<BF16>(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+        w.w = pack_p<BF16>(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
         *reinterpret_cast<uint4*>(dst + 8 * g) = w;
       }
     }
@@ -412,10 +518,21 @@ int attention_tc_launch(const void* q, const void* k, const void* v, void* o, in
     p.dbg = dbg_buf;
     g_attn_dbg = dbg_buf;
   }
-  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(flash_attn_tc_kernel), kSmemTotal + 1024);
+  // share of the exponentials evaluated on the FMA pipe, in eighths: CTTA_ATTN_POLY = 0 .. 4 -> 0 .. 50 % (A/B switch)
+  typedef void (*Fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+  static const Fn fns[2][5] = {{flash_attn_tc_kernel<0, 0, 0>, flash_attn_tc_kernel<1, 0, 0>, flash_attn_tc_kernel<2, 0, 0>,
+                                flash_attn_tc_kernel<3, 0, 0>, flash_attn_tc_kernel<4, 0, 0>},
+                               {flash_attn_tc_kernel<0, 1, 0>, flash_attn_tc_kernel<1, 1, 0>, flash_attn_tc_kernel<2, 1, 0>,
+                                flash_attn_tc_kernel<3, 1, 0>, flash_attn_tc_kernel<4, 1, 0>}};
+  int poly = kDefaultPoly;
+  if (const char* e = getenv("CTTA_ATTN_POLY")) poly = atoi(e);
+  if (poly < 0 || poly > 4) poly = kDefaultPoly;
+  Fn fn = fns[p.is_bf16 ? 1 : 0][poly];
+  if (p.dbg != nullptr) fn = p.is_bf16 ? flash_attn_tc_kernel<kDefaultPoly, 1, 1> : flash_attn_tc_kernel<kDefaultPoly, 0, 1>;
+  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(fn), kSmemTotal + 1024);
   if (rc) return rc;
   dim3 grid((lq + 2 * kTile - 1) / (2 * kTile), heads, batch);
-  flash_attn_tc_kernel<<<grid, kThreads, kSmemTotal + 1024, stream>>>(tq, tk, tv, p);
+  fn<<<grid, kThreads, kSmemTotal + 1024, stream>>>(tq, tk, tv, p);
   CTTA_LAUNCH_CHECK();
   return 0;
 }

@@ -493,11 +493,13 @@ def test_attention(b, h, lq, lk, masked):
 
 @pytest.mark.parametrize("b,h,lq,lk,masked,amp", [(2, 5, 4096, 4096, False, 1.0), (2, 3, 300, 500, True, 1.0),
                                                   (1, 2, 128, 128, False, 1.0), (2, 2, 640, 1152, True, 8.0),
-                                                  (1, 1, 256, 2048, False, 20.0)])
+                                                  (1, 1, 256, 2048, False, 20.0), (1, 2, 256, 1024, True, 80.0)])
 def test_attention_tcgen05_strided(b, h, lq, lk, masked, amp):
     """Self-attention sized problems run on the tcgen05 kernel: q/k/v are strided views of one fused buffer (the
-    UNet's qkv GEMM output); `amp` scales the scores so that the running max moves by more than the lazy-rescale
-    threshold between key tiles; ragged lq / lk exercise TMA zero fill and the key-length mask."""
+    UNet's qkv GEMM output); `amp` scales the scores so that later key tiles beat the running max: by more than 2^15
+    (amp 8 / 20: the optimistic tile evaluation fails its row-sum check and is redone against the true max) and by
+    more than 2^128 (amp 80: the optimistic exponentials overflow to inf); ragged lq / lk exercise TMA zero fill and the
+    key-length mask."""
     torch.manual_seed(12)
     d = 64
     lm = max(lq, lk)
