@@ -56,6 +56,8 @@ SIGNATURES = {
     "ctta_cfg_mix": (C.c_int, [_P, _I64, _F, _P, _P]),
     "ctta_tap_sum": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_int16), C.POINTER(C.c_int16), _P, _I32, _P, _P,
                                _I32, _P]),
+    "ctta_resblock_pair_supported": (C.c_int, [_I32, _I32, _I32, _I32]),
+    "ctta_resblock_pair": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _I32, _F, _P]),
     "ctta_mrf_combine": (C.c_int, [C.POINTER(C.c_void_p), _I32, _I64, _I32, _F, _F, _F, _P, _P]),
 }
 

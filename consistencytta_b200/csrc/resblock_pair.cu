@@ -1,0 +1,426 @@
+// Fused HiFi-GAN ResBlock pair for the narrow stages (C = 32 / 64):
+//
+//     x' = x + c2( lrelu( c1( lrelu(x) ) ) )        audioldm/hifigan/models.py:56-63 (one (c1, c2) pair of a ResBlock)
+//
+// in ONE kernel, on the LeakyReLU'ed 16-bit streams of vae.Generator.forward_btc: in = lx = lrelu(x) [B, T, C], out =
+// lrelu(x') [B, T, C]; c1 is the dilated conv (k taps, dilation d), c2 the plain one (k taps).  The unfused path runs two
+// implicit-GEMM launches and round-trips the hidden tensor through HBM (2+2 bytes per element for c1, 2+2+2 for c2);
+// here the hidden tile never leaves shared memory: HBM traffic is lx in + lrelu(x') out = 2+2 bytes per element.
+//
+// Tile = 256 rows of time (two 128-row UMMA tiles) of the hidden tensor h, i.e. L = 256 - (k - 1) output rows:
+//   X   TMA box of lx rows [t0 - p2 - p1, ...), p1 = d (k-1)/2, p2 = (k-1)/2, out-of-range rows zero filled (= the convs'
+//       zero padding), K-major SW128 rows of 128 B (C = 32: the upper 64 B are TMA zero fill and never read)
+//   c1  acc1[m] += X[rows m*128 + j*d ...] . W1[j]      tap j = a row-shifted UMMA view of the resident box
+//   E1  h = lrelu(acc1 + b1) (0 outside [0, T): c2's zero padding) -> 16-bit K-major SW128 tile H in shared memory
+//   c2  acc2[m] += H[rows m*128 + j ...] . W2[j]
+//   E2  lrelu(acc2 + b2 + x) with x = un-lrelu(lx) read back from the X box -> 16-bit staging tile -> TMA store of L rows
+// All taps of W1 and W2 stay resident in shared memory for the whole (persistent) CTA.  Warp roles: warp 0 = TMA
+// loader (X ring), warp 1 = single-thread tcgen05.mma issuer, warps 2..9 = epilogue (thread == row of one 128-row tile).
+// Tiles run through S "slots" (accumulators + H buffer) so that c1 of tile n + 1 runs under the epilogues of tile n.
+//
+// These stages are bound by the ~60-cycle issue floor of tcgen05.mma at N <= 64 (profiles/r1_umma_rate_microbench.txt),
+// not by HBM: the fusion removes the second launch's epilogue / HBM round trip, the MMA count stays.
+#include <cuda.h>
+#include <cstdlib>
+#include "ctta_internal.h"
+#include "ctta_ptx.cuh"
+
+namespace ctta {
+
+int make_tmap_ex(CUtensorMap* m, int dtype, CUtensorMapSwizzle swz, const void* base, int rank, const cuuint64_t* dims,
+                 const cuuint64_t* strides_bytes, const cuuint32_t* box);
+
+namespace rbp {
+
+constexpr int kThreads = 320;          // 10 warps
+constexpr int kEpiWarp0 = 2;           // warps 2..9
+constexpr int kHRows = 256;            // hidden rows per tile (two UMMA M tiles)
+constexpr int kHBufRows = 272;         // H buffer: the second M tile's taps read up to 10 rows past 256
+constexpr int kMaxX = 4, kMaxSlots = 2;
+
+struct Params {
+  int C, taps, dil, p1, p2, L;         // L = output rows per tile
+  int T, batch, tiles_per_seq, total_tiles;
+  int rx, rxh;                         // rows of the X box (two TMA boxes of rxh rows)
+  int n_x, n_slots;                    // X ring depth, accumulator / H slots
+  int w_tap_bytes;                     // C * 128
+  int off_w1, off_w2, off_x, x_bytes, off_h, h_bytes;
+  const float* b1;
+  const float* b2;
+  float slope, inv_slope;
+  int is_bf16;
+};
+
+struct Bars {
+  uint64_t w_full, x_full[kMaxX], x_empty[kMaxX], acc1_full[kMaxSlots], acc1_free[kMaxSlots], h_full[kMaxSlots],
+      h_free[kMaxSlots], acc2_full[kMaxSlots], acc2_free[kMaxSlots];
+};
+#define RB_BAR(field, idx) (bar_base + static_cast<uint32_t>(offsetof(Bars, field)) + 8u * static_cast<uint32_t>(idx))
+
+template <int BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  uint32_t r;
+  if (BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+template <int BF16>
+__device__ __forceinline__ void unpack2(uint32_t v, float& a, float& b) {
+  if (BF16) {
+    a = __uint_as_float(v << 16);
+    b = __uint_as_float(v & 0xFFFF0000u);
+  } else {
+    const __half2 h = *reinterpret_cast<const __half2*>(&v);
+    const float2 f = __half22float2(h);
+    a = f.x;
+    b = f.y;
+  }
+}
+__device__ __forceinline__ float lrelu(float v, float slope) { return v >= 0.f ? v : v * slope; }
+
+template <int C, int BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
+                     const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_out,
+                     const __grid_constant__ Params p) {
+  constexpr int KK = C / 16;            // 16-element K slices per tap
+  constexpr int NCH = C / 8;            // 16-byte chunks per row
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) Bars bars_s;
+  __shared__ float bias_s[2][64];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = pin_u32(smem_u32(&bars_s));
+  const int n_my = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int S = p.n_slots, NX = p.n_x;
+
+  if (threadIdx.x == 0) {
+    mbar_init(RB_BAR(w_full, 0), 1);
+    for (int i = 0; i < kMaxX; ++i) {
+      mbar_init(RB_BAR(x_full, i), 1);
+      mbar_init(RB_BAR(x_empty, i), 9);        // tcgen05.commit after c1 + the 8 epilogue warps after the residual read
+    }
+    for (int i = 0; i < kMaxSlots; ++i) {
+      mbar_init(RB_BAR(acc1_full, i), 1);
+      mbar_init(RB_BAR(acc1_free, i), 8);
+      mbar_init(RB_BAR(h_full, i), 8);
+      mbar_init(RB_BAR(h_free, i), 1);
+      mbar_init(RB_BAR(acc2_full, i), 1);
+      mbar_init(RB_BAR(acc2_free, i), 8);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_out);
+  }
+  if (threadIdx.x < 128) bias_s[threadIdx.x >> 6][threadIdx.x & 63] = (threadIdx.x & 63) < C ? ((threadIdx.x >> 6) ? p.b2 : p.b1)[threadIdx.x & 63] : 0.f;
+  const int tmem_cols = (S * 4 * C) <= 128 ? 128 : ((S * 4 * C) <= 256 ? 256 : 512);
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA loader: weights once, then the X ring
+    if (elect_one_sync()) {
+      const uint32_t wf = RB_BAR(w_full, 0);
+      mbar_arrive_expect_tx(wf, 2u * p.taps * p.w_tap_bytes);
+      for (int j = 0; j < p.taps; ++j) {
+        tma_load_2d(base + p.off_w1 + j * p.w_tap_bytes, &tmap_w1, wf, j * 64, 0);
+        tma_load_2d(base + p.off_w2 + j * p.w_tap_bytes, &tmap_w2, wf, j * 64, 0);
+      }
+      for (int n = 0; n < n_my; ++n) {
+        const int tile = blockIdx.x + n * gridDim.x;
+        const int b = tile / p.tiles_per_seq, t0 = (tile - b * p.tiles_per_seq) * p.L;
+        const int dx = n % NX;
+        mbar_wait(RB_BAR(x_empty, dx), static_cast<uint32_t>(((n / NX) & 1) ^ 1));
+        const uint32_t full = RB_BAR(x_full, dx);
+        mbar_arrive_expect_tx(full, static_cast<uint32_t>(p.rx) * 128u);
+        const uint32_t dst = base + p.off_x + dx * p.x_bytes;
+        const int r0 = t0 - p.p2 - p.p1;          // negative / past-the-end rows are zero filled by the TMA unit
+        tma_load_3d(dst, &tmap_x, full, 0, r0, b);
+        tma_load_3d(dst + p.rxh * 128, &tmap_x, full, 0, r0 + p.rxh, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one_sync()) {
+      const uint32_t idesc = umma_idesc(128, C, BF16);
+      mbar_wait(RB_BAR(w_full, 0), 0);
+      const uint32_t w1_lo = umma_desc_lo(base + p.off_w1), w2_lo = umma_desc_lo(base + p.off_w2);
+      const uint32_t w_step = static_cast<uint32_t>(p.w_tap_bytes) >> 4;
+      for (int n = 0; n < n_my + S - 1; ++n) {
+        if (n < n_my) {
+          // c1 of tile n: tap j = the X box shifted by j * d rows of 128 bytes (the swizzle phase follows the address bits)
+          const int s = n % S, dx = n % NX;
+          mbar_wait(RB_BAR(x_full, dx), static_cast<uint32_t>((n / NX) & 1));
+          mbar_wait(RB_BAR(acc1_free, s), static_cast<uint32_t>(((n / S) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t x_lo = umma_desc_lo(base + p.off_x + dx * p.x_bytes);
+#pragma unroll 1
+          for (int m = 0; m < 2; ++m) {
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(s * 4 * C + m * C);
+#pragma unroll 1
+            for (int j = 0; j < p.taps; ++j) {
+              const uint32_t a_lo = x_lo + static_cast<uint32_t>(m * 128 + j * p.dil) * 8u;
+              const uint32_t b_lo = w1_lo + static_cast<uint32_t>(j) * w_step;
+#pragma unroll
+              for (int kk = 0; kk < KK; ++kk)
+                umma_f16(d_tmem, umma_desc_from_lo(a_lo + 2 * kk), umma_desc_from_lo(b_lo + 2 * kk), idesc, (j | kk) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(RB_BAR(acc1_full, s));
+          umma_commit(RB_BAR(x_empty, dx));
+        }
+        const int i2 = n - (S - 1);
+        if (i2 >= 0 && i2 < n_my) {
+          // c2 of tile i2 on the hidden tile the epilogue warps wrote
+          const int s = i2 % S;
+          mbar_wait(RB_BAR(h_full, s), static_cast<uint32_t>((i2 / S) & 1));
+          mbar_wait(RB_BAR(acc2_free, s), static_cast<uint32_t>(((i2 / S) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t h_lo = umma_desc_lo(base + p.off_h + s * p.h_bytes);
+#pragma unroll 1
+          for (int m = 0; m < 2; ++m) {
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(s * 4 * C + 2 * C + m * C);
+#pragma unroll 1
+            for (int j = 0; j < p.taps; ++j) {
+              const uint32_t a_lo = h_lo + static_cast<uint32_t>(m * 128 + j) * 8u;
+              const uint32_t b_lo = w2_lo + static_cast<uint32_t>(j) * w_step;
+#pragma unroll
+              for (int kk = 0; kk < KK; ++kk)
+                umma_f16(d_tmem, umma_desc_from_lo(a_lo + 2 * kk), umma_desc_from_lo(b_lo + 2 * kk), idesc, (j | kk) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(RB_BAR(acc2_full, s));
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps: thread == row of one 128-row tile
+    const int e = warp - kEpiWarp0;
+    const int m = e >> 2;                           // which of the two 128-row tiles
+    const int q = warp & 3;                         // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;
+    const int hr = m * 128 + row;                   // row of the 256-row hidden / output tile
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const float slope = p.slope, inv_slope = p.inv_slope;
+    for (int n = 0; n < n_my + S - 1; ++n) {
+      if (n < n_my) {
+        // ---- E1: h = lrelu(c1 + b1), zero outside the sequence, -> K-major SW128 tile
+        const int s = n % S;
+        const int tile = blockIdx.x + n * gridDim.x;
+        const int b = tile / p.tiles_per_seq, t0 = (tile - b * p.tiles_per_seq) * p.L;
+        mbar_wait(RB_BAR(acc1_full, s), static_cast<uint32_t>((n / S) & 1));
+        tc_fence_after();
+        uint32_t u[C];
+        const uint32_t a1 = tmem_base + lane_addr + static_cast<uint32_t>(s * 4 * C + m * C);
+        tmem_ld_x32(a1, u);
+        if (C == 64) tmem_ld_x32(a1 + 32, u + (C == 64 ? 32 : 0));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(RB_BAR(acc1_free, s));
+        const int th = t0 - p.p2 + hr;
+        const bool valid = th >= 0 && th < p.T;
+        mbar_wait(RB_BAR(h_free, s), static_cast<uint32_t>(((n / S) & 1) ^ 1));   // the TMA store that staged in this buffer has read it
+        const uint32_t h_row = base + p.off_h + s * p.h_bytes + static_cast<uint32_t>(hr) * 128u;
+        const uint32_t xr = static_cast<uint32_t>(hr & 7);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c0 = 8 * ch + 2 * i;
+            const float v0 = valid ? lrelu(__uint_as_float(u[c0]) + bias_s[0][c0], slope) : 0.f;
+            const float v1 = valid ? lrelu(__uint_as_float(u[c0 + 1]) + bias_s[0][c0 + 1], slope) : 0.f;
+            w[i] = pack2<BF16>(v0, v1);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_row + ((static_cast<uint32_t>(ch) ^ xr) << 4)),
+                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(RB_BAR(h_full, s));
+      }
+      const int i2 = n - (S - 1);
+      if (i2 >= 0 && i2 < n_my) {
+        // ---- E2: lrelu(c2 + b2 + x), x recovered from the lrelu'ed input rows still resident in the X box
+        const int s = i2 % S, dx = i2 % NX;
+        const int tile = blockIdx.x + i2 * gridDim.x;
+        const int b = tile / p.tiles_per_seq, t0 = (tile - b * p.tiles_per_seq) * p.L;
+        mbar_wait(RB_BAR(acc2_full, s), static_cast<uint32_t>((i2 / S) & 1));
+        tc_fence_after();
+        uint32_t u[C];
+        const uint32_t a2 = tmem_base + lane_addr + static_cast<uint32_t>(s * 4 * C + 2 * C + m * C);
+        tmem_ld_x32(a2, u);
+        if (C == 64) tmem_ld_x32(a2 + 32, u + (C == 64 ? 32 : 0));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(RB_BAR(acc2_free, s));
+        // residual: X row of output row hr is hr + p2 + p1
+        const int xrow = hr + p.p2 + p.p1;
+        const uint32_t x_row = base + p.off_x + dx * p.x_bytes + static_cast<uint32_t>(xrow) * 128u;
+        const uint32_t xx = static_cast<uint32_t>(xrow & 7);
+        // staging tile: dense rows of 2 C bytes, SW128 on the linear address (what the TMA store un-swizzles)
+        const uint32_t st_base = base + p.off_h + s * p.h_bytes;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t r0, r1, r2, r3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                       : "r"(x_row + ((static_cast<uint32_t>(ch) ^ xx) << 4)));
+          const uint32_t rr[4] = {r0, r1, r2, r3};
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c0 = 8 * ch + 2 * i;
+            float x0, x1;
+            unpack2<BF16>(rr[i], x0, x1);
+            x0 = x0 >= 0.f ? x0 : x0 * inv_slope;
+            x1 = x1 >= 0.f ? x1 : x1 * inv_slope;
+            const float v0 = lrelu(__uint_as_float(u[c0]) + bias_s[1][c0] + x0, slope);
+            const float v1 = lrelu(__uint_as_float(u[c0 + 1]) + bias_s[1][c0 + 1] + x1, slope);
+            w[i] = pack2<BF16>(v0, v1);
+          }
+          const uint32_t lin = static_cast<uint32_t>(hr) * (2u * C) + static_cast<uint32_t>(ch) * 16u;
+          const uint32_t phys = lin ^ (((lin >> 7) & 7u) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_base + phys), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                       "r"(w[3]) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(RB_BAR(x_empty, dx));      // this warp no longer reads the X box
+        named_barrier_sync(1, 256);                            // all 8 epilogue warps have staged their rows
+        if (e == 0 && lane == 0) {   // always the same thread: bulk async-groups are per thread (wait_read / wait_all below)
+          tma_store_3d(&tmap_out, st_base, 0, C == 64 ? t0 : t0 / 2, b);   // L rows (C = 32: L / 2 row pairs); rows past the end of the sequence are clipped
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          mbar_arrive(RB_BAR(h_free, s));
+        }
+      }
+    }
+    if (e == 0 && lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace rbp
+}  // namespace ctta
+
+using namespace ctta;
+
+extern "C" int ctta_resblock_pair_supported(int32_t c, int32_t taps, int32_t dilation, int32_t t) {
+  if (c != 32 && c != 64) return 0;
+  if (c == 32 && (t & 1)) return 0;     // the 64-byte output rows are stored pairwise as [t / 2, 64] (128-byte TMA rows)
+  if (taps < 3 || taps > 11 || (taps & 1) == 0 || dilation < 1) return 0;
+  if (dilation * (taps - 1) > 56) return 0;
+  // resident weights of both convs + at least two X boxes + one H buffer must fit shared memory
+  const int w = 2 * taps * c * 128;
+  const int rx = (256 + dilation * (taps - 1) + 15) / 16 * 16;
+  return (w + 2 * rx * 128 + rbp::kHBufRows * 128 + 4096 <= 227 * 1024) ? 1 : 0;
+}
+
+extern "C" int ctta_resblock_pair(const void* x, void* out, int32_t dtype, int32_t batch, int32_t t, int32_t c,
+                                  const void* w1, const float* b1, const void* w2, const float* b2, int32_t taps,
+                                  int32_t dilation, float slope, void* stream_v) {
+  using namespace rbp;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  CTTA_REQUIRE(x && out && w1 && w2 && b1 && b2, "resblock_pair: null argument");
+  CTTA_REQUIRE(dtype == CTTA_F16 || dtype == CTTA_BF16, "resblock_pair: 16-bit streams only");
+  CTTA_REQUIRE(batch > 0 && t > 0 && slope > 0.f, "resblock_pair: bad shape / slope");
+  if (!ctta_resblock_pair_supported(c, taps, dilation, t))
+    return set_error(CTTA_ERR_UNSUPPORTED, "resblock_pair: c=%d taps=%d dilation=%d not supported", c, taps, dilation);
+  for (const void* ptr : {x, static_cast<const void*>(out), w1, w2})
+    CTTA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "resblock_pair: operands must be 16-byte aligned");
+  Params p{};
+  p.C = c;
+  p.taps = taps;
+  p.dil = dilation;
+  p.p2 = (taps - 1) / 2;
+  p.p1 = p.p2 * dilation;
+  p.L = kHRows - (taps - 1);
+  p.T = t;
+  p.batch = batch;
+  p.tiles_per_seq = (t + p.L - 1) / p.L;
+  p.total_tiles = p.tiles_per_seq * batch;
+  p.rx = (kHRows + 2 * p.p1 + 15) / 16 * 16;
+  p.rxh = p.rx / 2;
+  p.w_tap_bytes = c * 128;
+  p.b1 = b1;
+  p.b2 = b2;
+  p.slope = slope;
+  p.inv_slope = 1.f / slope;
+  p.is_bf16 = dtype == CTTA_BF16;
+  // shared-memory plan: W1 | W2 | X ring | H slots, every region 1024-byte aligned
+  const int w_bytes = (taps * p.w_tap_bytes + 1023) / 1024 * 1024;
+  p.x_bytes = (p.rx * 128 + 1023) / 1024 * 1024;
+  p.h_bytes = (kHBufRows * 128 + 1023) / 1024 * 1024;
+  const int budget = 227 * 1024 - 4096 - 2 * w_bytes;   // 1 KiB alignment slack + static barriers / biases
+  int slots = 2, nx = 3;
+  if (const char* e = getenv("CTTA_RBP_SLOTS")) slots = atoi(e) == 1 ? 1 : 2;
+  while (true) {
+    if (slots * p.h_bytes + nx * p.x_bytes <= budget) break;
+    if (nx > 2) --nx;
+    else if (slots > 1) { slots = 1; nx = 3; }
+    else return set_error(CTTA_ERR_UNSUPPORTED, "resblock_pair: shared memory plan does not fit");
+  }
+  if (slots * 4 * c > 512) slots = 1;
+  p.n_slots = slots;
+  p.n_x = nx;
+  p.off_w1 = 0;
+  p.off_w2 = w_bytes;
+  p.off_x = 2 * w_bytes;
+  p.off_h = p.off_x + nx * p.x_bytes;
+  const int smem_bytes = p.off_h + slots * p.h_bytes + 1024;
+
+  CUtensorMap tx, tw1, tw2, tout;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)c, (cuuint64_t)t, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)c * 2, (cuuint64_t)c * 2 * (cuuint64_t)t};
+    cuuint32_t box[3] = {64, (cuuint32_t)p.rxh, 1};
+    int rc = make_tmap_ex(&tx, dtype, CU_TENSOR_MAP_SWIZZLE_128B, x, 3, dims, strides, box);
+    if (rc) return rc;
+    if (c == 64) {
+      cuuint32_t obox[3] = {64, (cuuint32_t)p.L, 1};
+      rc = make_tmap_ex(&tout, dtype, CU_TENSOR_MAP_SWIZZLE_128B, out, 3, dims, strides, obox);
+    } else {
+      // C = 32: rows of 64 B are stored pairwise, the tensor viewed as [t / 2, 64] (same memory; L and every t0 are even)
+      cuuint64_t pd[3] = {64, (cuuint64_t)t / 2, (cuuint64_t)batch};
+      cuuint64_t ps[2] = {128, (cuuint64_t)t * 64};
+      cuuint32_t obox[3] = {64, (cuuint32_t)p.L / 2, 1};
+      rc = make_tmap_ex(&tout, dtype, CU_TENSOR_MAP_SWIZZLE_128B, out, 3, pd, ps, obox);
+    }
+    if (rc) return rc;
+    // packed weights [n = C, taps * 64] (ops.pack_conv1d): tap j is the {64 x C} box at column 64 j
+    cuuint64_t wd[2] = {(cuuint64_t)taps * 64, (cuuint64_t)c};
+    cuuint64_t ws[1] = {(cuuint64_t)taps * 64 * 2};
+    cuuint32_t wb[2] = {64, (cuuint32_t)c};
+    rc = make_tmap_ex(&tw1, dtype, CU_TENSOR_MAP_SWIZZLE_128B, w1, 2, wd, ws, wb);
+    if (rc) return rc;
+    rc = make_tmap_ex(&tw2, dtype, CU_TENSOR_MAP_SWIZZLE_128B, w2, 2, wd, ws, wb);
+    if (rc) return rc;
+  }
+  typedef void (*Fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+  Fn fn = c == 32 ? (p.is_bf16 ? resblock_pair_kernel<32, 1> : resblock_pair_kernel<32, 0>)
+                  : (p.is_bf16 ? resblock_pair_kernel<64, 1> : resblock_pair_kernel<64, 0>);
+  int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024 - 2048);
+  if (rc) return rc;
+  int grid = sm_count();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  fn<<<grid, kThreads, smem_bytes, stream>>>(tx, tw1, tw2, tout, p);
+  CTTA_LAUNCH_CHECK();
+  return 0;
+}

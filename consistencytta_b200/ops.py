@@ -488,6 +488,28 @@ def lrelu_cast(x, slope, out=None):
     return out
 
 
+def resblock_pair_supported(c, taps, dilation, t=2):
+    return bool(lib().ctta_resblock_pair_supported(c, taps, dilation, t))
+
+
+def resblock_pair(lx, pw1, pw2, slope, out=None):
+    """One fused (c1, c2) pair of a HiFi-GAN ResBlock (hifigan/models.py:56-63) on the LeakyReLU'ed 16-bit stream:
+    lx = lrelu(x) [B, T, C] -> lrelu(x + c2(lrelu(c1(lrelu(x))))) [B, T, C].  pw1 / pw2 from pack_conv1d (pw1 dilated)."""
+    _require_cuda(lx)
+    b, t, c = lx.shape
+    assert lx.is_contiguous() and pw1.ntaps == pw2.ntaps and pw1.n == c and pw2.n == c and pw1.c == c and pw2.c == c
+    assert pw1.w.dtype == lx.dtype and pw2.w.dtype == lx.dtype and pw1.bias is not None and pw2.bias is not None
+    taps = pw1.ntaps
+    dil = (pw1.d0[1] - pw1.d0[0]) if taps > 1 else 1
+    assert (pw2.d0[1] - pw2.d0[0] if taps > 1 else 1) == 1, "c2 is the undilated conv"
+    if out is None:
+        out = torch.empty_like(lx)
+    assert out.is_contiguous() and out.shape == lx.shape and out.dtype == lx.dtype and out.data_ptr() != lx.data_ptr()
+    check(lib().ctta_resblock_pair(_ptr(lx), _ptr(out), _DT[lx.dtype], b, t, c, _ptr(pw1.w), _ptr(pw1.bias), _ptr(pw2.w),
+                                   _ptr(pw2.bias), taps, dil, slope, _stream()))
+    return out
+
+
 def mrf_combine(xs, in_slope, out_scale, out_slope, out=None):
     """HiFi-GAN MRF sum over the LeakyReLU'ed 16-bit ResBlock outputs `xs` -> LeakyReLU'ed 16-bit operand of the next stage."""
     x0 = xs[0]

@@ -5,6 +5,8 @@ decode_to_waveform, .decoder/.post_quant_conv/.vocoder/.scale_factor), modules.p
 audioldm/hifigan/models.py:66-117 (Generator) with the reference's state_dict keys.  The encode side
 (encoder.*, quant_conv.*) is training/eval only and out of scope: its keys are accepted and ignored.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -26,6 +28,8 @@ class Generator(PackedModule):
             self.h.update({k: h[k] for k in weights.HIFIGAN_CONFIG if k in h})
         self.num_kernels = len(self.h["resblock_kernel_sizes"])
         self.num_upsamples = len(self.h["upsample_rates"])
+        # fused ResBlock-pair kernel on the C <= 64 stages (False / CTTA_NO_FUSE_PAIRS=1: two ctta_gemm launches per pair)
+        self.fuse_pairs = os.environ.get("CTTA_NO_FUSE_PAIRS") is None
         register_tree(self, weights.vocoder_schema(self.h, prefix=""))
 
     def remove_weight_norm(self):
@@ -83,8 +87,14 @@ class Generator(PackedModule):
                 n = i * nk + j
                 cur = lx
                 for m in range(3):
-                    ops.conv1d(cur, pk["rb.%d.c1.%d" % (n, m)], out2=tmp16, act2=ACT_LRELU, act2_slope=slope)
                     dst = branch[j] if m == 2 else ping[m]
+                    pw1, pw2 = pk["rb.%d.c1.%d" % (n, m)], pk["rb.%d.c2.%d" % (n, m)]
+                    if self.fuse_pairs and ops.resblock_pair_supported(c, pw1.ntaps, pw1.d0[1] - pw1.d0[0], t):
+                        # narrow stages (C <= 64): c1 -> lrelu -> c2 -> + x in ONE kernel, hidden tile in shared memory
+                        ops.resblock_pair(cur, pw1, pw2, slope, out=dst)
+                        cur = dst
+                        continue
+                    ops.conv1d(cur, pw1, out2=tmp16, act2=ACT_LRELU, act2_slope=slope)
                     # x' = x + c2(lrelu(c1(lrelu(x)))) with x recovered from lrelu(x); emitted again as lrelu(x')
                     ops.conv1d(tmp16, pk["rb.%d.c2.%d" % (n, m)], residual=cur, res_neg_scale=1.0 / slope, out2=dst,
                                act2=ACT_LRELU, act2_slope=slope)

@@ -210,6 +210,18 @@ int ctta_wave_to_int16(const float* wav, int64_t numel, const float* minmax, int
  * (audioldm/hifigan/models.py:104,112-113). */
 int ctta_lrelu_cast(const float* x, int64_t numel, float slope, void* y, int32_t y_dtype, void* stream);
 
+/* One (c1, c2) pair of a HiFi-GAN ResBlock fused in a single kernel (audioldm/hifigan/models.py:56-63):
+ *     x' = x + c2( lrelu( c1( lrelu(x) ) ) ),  c1 = Conv1d(C, C, taps, dilation, "same"), c2 = Conv1d(C, C, taps, 1, "same")
+ * on the LeakyReLU'ed 16-bit streams of the vocoder: x_lrelu = lrelu(x, slope) [batch, t, c] in, out = lrelu(x', slope)
+ * [batch, t, c]; w1 / w2 are K-major packed weights [c, taps * 64] (taps of 64 zero-padded input channels each), b1 / b2
+ * fp32 [c].  The hidden tensor lives only in shared memory.  ctta_resblock_pair_supported() tells whether a
+ * (c, taps, dilation) fits (c in {32, 64}, odd taps <= 11, even t for c = 32, resident weights + tiles within 227 KiB); otherwise the two
+ * convolutions run through ctta_gemm.  Returns CTTA_ERR_UNSUPPORTED for an unsupported combination. */
+int ctta_resblock_pair_supported(int32_t c, int32_t taps, int32_t dilation, int32_t t);
+int ctta_resblock_pair(const void* x_lrelu, void* out, int32_t dtype, int32_t batch, int32_t t, int32_t c, const void* w1,
+                       const float* b1, const void* w2, const float* b2, int32_t taps, int32_t dilation, float slope,
+                       void* stream);
+
 /* HiFi-GAN multi-receptive-field sum (audioldm/hifigan/models.py:106-112 followed by the LeakyReLU at :104 / :113):
  * the n_in (<= 4) ResBlock outputs arrive as their LeakyReLU'ed 16-bit copies (negative values scaled by in_slope);
  * y = 16-bit( lrelu( out_scale * sum_i lrelu^-1(x_i), out_slope ) ), the operand of the next up-sampling stage. */

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-from consistencytta_b200 import ops  # noqa: E402
+from consistencytta_b200 import _lib, ops  # noqa: E402
 
 DEV = "cuda"
 DT = ops.OPERAND_DTYPE
@@ -173,6 +173,49 @@ def test_conv1d_lrelu_residual_stream(k, dil, c, t, bsz):
     x_rec = torch.where(lxf < 0, lxf / slope, lxf)
     ref = F.conv1d(a.permute(0, 2, 1), wt, b, dilation=dil, padding=(k * dil - dil) // 2).permute(0, 2, 1) + x_rec
     assert rel(out2, F.leaky_relu(ref, slope)) < 1e-3
+
+
+@pytest.mark.parametrize("c,k,dil,t,bsz", [(32, 3, 1, 1000, 2), (32, 11, 5, 5000, 2), (64, 7, 3, 2500, 3), (64, 3, 5, 300, 2),
+                                           (32, 7, 1, 40968, 2), (32, 11, 1, 246, 1), (64, 7, 5, 251, 2), (32, 3, 3, 18, 3),
+                                           (64, 3, 1, 81936, 3), (32, 11, 3, 163872, 2)])
+def test_resblock_pair_fused(c, k, dil, t, bsz):
+    """One (c1, c2) pair of a HiFi-GAN ResBlock in ONE kernel (hidden tile in shared memory) against F.conv1d in fp32
+    (hifigan/models.py:56-63), on the LeakyReLU'ed 16-bit streams; also against the two-launch ctta_gemm path it replaces.
+    Sequence lengths around the 256 - (k - 1) row tile exercise the zero padding of BOTH convs at the sequence ends."""
+    torch.manual_seed(41)
+    slope = 0.1
+    assert ops.resblock_pair_supported(c, k, dil, t)
+    x = torch.randn(bsz, t, c, device=DEV)
+    lx = F.leaky_relu(x, slope).to(DT)
+    w1 = r16(torch.randn(c, c, k, device=DEV) / math.sqrt(k * c))
+    w2 = r16(torch.randn(c, c, k, device=DEV) / math.sqrt(k * c))
+    b1, b2 = torch.randn(c, device=DEV) * 0.1, torch.randn(c, device=DEV) * 0.1
+    pw1, pw2 = ops.pack_conv1d(w1, b1, dilation=dil), ops.pack_conv1d(w2, b2, dilation=1)
+    out = ops.resblock_pair(lx, pw1, pw2, slope)
+    assert out.shape == lx.shape and out.dtype == DT and torch.isfinite(out.float()).all()
+    lxf = lx.float()
+    x_rec = torch.where(lxf < 0, lxf / slope, lxf)
+    h = F.conv1d(lxf.permute(0, 2, 1), w1, b1, dilation=dil, padding=(k * dil - dil) // 2)
+    h16 = r16(F.leaky_relu(h, slope))                       # the hidden tensor is held in 16 bits (as in the unfused path)
+    y = x_rec.permute(0, 2, 1) + F.conv1d(h16, w2, b2, padding=(k - 1) // 2)
+    ref = F.leaky_relu(y, slope).permute(0, 2, 1)
+    e = rel(out, ref)
+    assert e < 1e-3, e
+    # the unfused path: two implicit-GEMM launches with the hidden tensor in HBM
+    tmp = torch.empty_like(lx)
+    two = torch.empty_like(lx)
+    ops.conv1d(lx, pw1, out2=tmp, act2=ops.ACT_LRELU, act2_slope=slope)
+    ops.conv1d(tmp, pw2, residual=lx, res_neg_scale=1.0 / slope, out2=two, act2=ops.ACT_LRELU, act2_slope=slope)
+    assert rel(out, two) < 1e-3
+
+
+def test_resblock_pair_unsupported_shapes_are_refused():
+    assert not ops.resblock_pair_supported(64, 11, 1)        # resident weights of both convs exceed shared memory
+    assert not ops.resblock_pair_supported(128, 3, 1) and not ops.resblock_pair_supported(32, 4, 1) and not ops.resblock_pair_supported(32, 3, 1, 1001)
+    lx = torch.zeros(1, 64, 128, device=DEV, dtype=DT)
+    pw = ops.pack_conv1d(torch.zeros(128, 128, 3, device=DEV), torch.zeros(128, device=DEV))
+    with pytest.raises(_lib.CttaError):
+        ops.resblock_pair(lx, pw, pw, 0.1)
 
 
 @pytest.mark.parametrize("kind", ["conv1d_stream", "linear", "conv2d_stream"])
