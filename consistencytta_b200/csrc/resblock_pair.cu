@@ -78,11 +78,11 @@ __device__ __forceinline__ void unpack2(uint32_t v, float& a, float& b) {
 }
 __device__ __forceinline__ float lrelu(float v, float slope) { return v >= 0.f ? v : v * slope; }
 
-template <int C, int BF16>
+template <int C, int BF16, int S>
 __global__ void __launch_bounds__(kThreads, 1)
 resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
                      const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_out,
-                     const __grid_constant__ Params p) {
+                     const __grid_constant__ CUtensorMap tmap_tail, const __grid_constant__ Params p) {
   constexpr int KK = C / 16;            // 16-element K slices per tap
   constexpr int NCH = C / 8;            // 16-byte chunks per row
   extern __shared__ uint8_t smem_raw[];
@@ -95,19 +95,19 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = pin_u32(smem_u32(&bars_s));
   const int n_my = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int S = p.n_slots, NX = p.n_x;
+  const int NX = p.n_x;          // S (accumulator / H slots) is a template parameter: the epilogue's register sets are picked statically
 
   if (threadIdx.x == 0) {
     mbar_init(RB_BAR(w_full, 0), 1);
     for (int i = 0; i < kMaxX; ++i) {
       mbar_init(RB_BAR(x_full, i), 1);
-      mbar_init(RB_BAR(x_empty, i), 9);        // tcgen05.commit after c1 + the 8 epilogue warps after the residual read
+      mbar_init(RB_BAR(x_empty, i), 8);        // the 8 epilogue warps, once c1 has completed and their residual rows are in registers
     }
     for (int i = 0; i < kMaxSlots; ++i) {
       mbar_init(RB_BAR(acc1_full, i), 1);
       mbar_init(RB_BAR(acc1_free, i), 8);
       mbar_init(RB_BAR(h_full, i), 8);
-      mbar_init(RB_BAR(h_free, i), 1);
+      mbar_init(RB_BAR(h_free, i), 8);         // every epilogue warp, once its TMA store has read its staging rows
       mbar_init(RB_BAR(acc2_full, i), 1);
       mbar_init(RB_BAR(acc2_free, i), 8);
     }
@@ -176,7 +176,6 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             }
           }
           umma_commit(RB_BAR(acc1_full, s));
-          umma_commit(RB_BAR(x_empty, dx));
         }
         const int i2 = n - (S - 1);
         if (i2 >= 0 && i2 < n_my) {
@@ -211,25 +210,71 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const int hr = m * 128 + row;                   // row of the 256-row hidden / output tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const float slope = p.slope, inv_slope = p.inv_slope;
-    for (int n = 0; n < n_my + S - 1; ++n) {
+    // One step of the epilogue schedule: E1 of tile n (if any), then E2 of tile n - (S - 1) (if any).  The residual rows of
+    // a tile are pulled out of its X box into registers during E1 (`res_new`), so the box goes back to the loader as soon
+    // as c1 has consumed it instead of being held until E2; with S = 2 the E2 of a step belongs to the PREVIOUS tile, whose
+    // rows are in the other register set (`res_old`) — hence the two-step unrolled loop below.
+    int pending_slot = -1;   // slot whose staging rows this warp's last TMA store may still be reading
+    auto step = [&](int n, uint32_t (&res_new)[C / 2], uint32_t (&res_old)[C / 2]) {
       if (n < n_my) {
         // ---- E1: h = lrelu(c1 + b1), zero outside the sequence, -> K-major SW128 tile
-        const int s = n % S;
+        const int s = n % S, dx = n % NX;
         const int tile = blockIdx.x + n * gridDim.x;
         const int b = tile / p.tiles_per_seq, t0 = (tile - b * p.tiles_per_seq) * p.L;
         mbar_wait(RB_BAR(acc1_full, s), static_cast<uint32_t>((n / S) & 1));
         tc_fence_after();
+        __syncwarp();          // tcgen05.ld is warp-collective (.sync.aligned): reconverge after the divergent wait loop
         uint32_t u[C];
         const uint32_t a1 = tmem_base + lane_addr + static_cast<uint32_t>(s * 4 * C + m * C);
         tmem_ld_x32(a1, u);
         if (C == 64) tmem_ld_x32(a1 + 32, u + (C == 64 ? 32 : 0));
+        // residual rows (lrelu'ed input of output row hr = X row hr + p2 + p1) while the TMEM load is in flight.
+        // The box was written by the TMA unit (async proxy): a thread that reads it with ordinary loads has to observe the
+        // box's own mbarrier ITSELF — knowing through acc1_full that the issuer saw it complete is not enough (without this
+        // wait, rows of the box came back with the contents of an earlier launch).  The phase has completed long ago.
+        mbar_wait(RB_BAR(x_full, dx), static_cast<uint32_t>((n / NX) & 1));
+        {
+          const int xrow = hr + p.p2 + p.p1;
+          const uint32_t x_row = base + p.off_x + dx * p.x_bytes + static_cast<uint32_t>(xrow) * 128u;
+          const uint32_t xx = static_cast<uint32_t>(xrow & 7);
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(res_new[4 * ch]), "=r"(res_new[4 * ch + 1]), "=r"(res_new[4 * ch + 2]), "=r"(res_new[4 * ch + 3])
+                         : "r"(x_row + ((static_cast<uint32_t>(ch) ^ xx) << 4))
+                         : "memory");
+        }
         tmem_ld_wait();
+        // The box is handed back below, and the loader's next TMA write may follow within a microsecond.  An issued
+        // ld.shared is NOT a completed one: the arrive was observed to overtake loads still queued in the memory pipeline
+        // (the residual of tile n then came from tile n + NX).  Instructions that CONSUME the loaded registers cannot issue
+        // before the data is back, and the warp issues in order — so the arrive's ADDRESS is made to depend on a fold of them.
+        uint32_t dep;
+        {
+          uint32_t f = 0;
+#pragma unroll
+          for (int i = 0; i < C / 2; ++i) f ^= res_new[i];
+          f = __reduce_or_sync(0xffffffffu, f);                         // every lane's loads
+          asm volatile("and.b32 %0, %1, 0;" : "=r"(dep) : "r"(f));      // opaque 0 that depends on them
+        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(RB_BAR(acc1_free, s));
+        if (lane == 0) {
+          mbar_arrive(RB_BAR(acc1_free, s));
+          mbar_arrive(RB_BAR(x_empty, dx) + dep);      // c1 has completed (acc1_full) and this warp has its residual rows
+        }
         const int th = t0 - p.p2 + hr;
         const bool valid = th >= 0 && th < p.T;
-        mbar_wait(RB_BAR(h_free, s), static_cast<uint32_t>(((n / S) & 1) ^ 1));   // the TMA store that staged in this buffer has read it
+        // hand back the staging rows of this warp's previous TMA store: by now (one TMEM load later) it has read them
+        if (pending_slot >= 0) {
+          if (lane == 0) {
+            tma_store_wait_read<0>();
+            mbar_arrive(RB_BAR(h_free, pending_slot));
+          }
+          pending_slot = -1;
+          __syncwarp();
+        }
+        mbar_wait(RB_BAR(h_free, s), static_cast<uint32_t>(((n / S) & 1) ^ 1));   // every warp's store out of this buffer has read it
         const uint32_t h_row = base + p.off_h + s * p.h_bytes + static_cast<uint32_t>(hr) * 128u;
         const uint32_t xr = static_cast<uint32_t>(hr & 7);
 #pragma unroll
@@ -251,12 +296,14 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       }
       const int i2 = n - (S - 1);
       if (i2 >= 0 && i2 < n_my) {
-        // ---- E2: lrelu(c2 + b2 + x), x recovered from the lrelu'ed input rows still resident in the X box
-        const int s = i2 % S, dx = i2 % NX;
+        // ---- E2: lrelu(c2 + b2 + x), x recovered from the lrelu'ed input rows held in registers since E1
+        uint32_t (&res)[C / 2] = *(S == 2 ? &res_old : &res_new);
+        const int s = i2 % S;
         const int tile = blockIdx.x + i2 * gridDim.x;
         const int b = tile / p.tiles_per_seq, t0 = (tile - b * p.tiles_per_seq) * p.L;
         mbar_wait(RB_BAR(acc2_full, s), static_cast<uint32_t>((i2 / S) & 1));
         tc_fence_after();
+        __syncwarp();
         uint32_t u[C];
         const uint32_t a2 = tmem_base + lane_addr + static_cast<uint32_t>(s * 4 * C + 2 * C + m * C);
         tmem_ld_x32(a2, u);
@@ -265,24 +312,16 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(RB_BAR(acc2_free, s));
-        // residual: X row of output row hr is hr + p2 + p1
-        const int xrow = hr + p.p2 + p.p1;
-        const uint32_t x_row = base + p.off_x + dx * p.x_bytes + static_cast<uint32_t>(xrow) * 128u;
-        const uint32_t xx = static_cast<uint32_t>(xrow & 7);
         // staging tile: dense rows of 2 C bytes, SW128 on the linear address (what the TMA store un-swizzles)
         const uint32_t st_base = base + p.off_h + s * p.h_bytes;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-          uint32_t r0, r1, r2, r3;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                       : "r"(x_row + ((static_cast<uint32_t>(ch) ^ xx) << 4)));
-          const uint32_t rr[4] = {r0, r1, r2, r3};
           uint32_t w[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int c0 = 8 * ch + 2 * i;
             float x0, x1;
-            unpack2<BF16>(rr[i], x0, x1);
+            unpack2<BF16>(res[4 * ch + i], x0, x1);
             x0 = x0 >= 0.f ? x0 : x0 * inv_slope;
             x1 = x1 >= 0.f ? x1 : x1 * inv_slope;
             const float v0 = lrelu(__uint_as_float(u[c0]) + bias_s[1][c0] + x0, slope);
@@ -296,17 +335,26 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(RB_BAR(x_empty, dx));      // this warp no longer reads the X box
-        named_barrier_sync(1, 256);                            // all 8 epilogue warps have staged their rows
-        if (e == 0 && lane == 0) {   // always the same thread: bulk async-groups are per thread (wait_read / wait_all below)
-          tma_store_3d(&tmap_out, st_base, 0, C == 64 ? t0 : t0 / 2, b);   // L rows (C = 32: L / 2 row pairs); rows past the end of the sequence are clipped
+        // every warp stores its own 32 rows (no CTA-wide rendezvous): rows >= L belong to the next tile, so the warp that
+        // straddles L uses the shorter box and the ones past it store nothing; rows past the end of the sequence are clipped
+        if (lane == 0) {     // always the same thread: bulk async-groups are per thread (wait_read / wait_all)
+          const int r0 = m * 128 + q * 32;
+          const uint32_t src = st_base + static_cast<uint32_t>(r0) * (2u * C);
+          if (r0 + 32 <= p.L) tma_store_3d(&tmap_out, src, 0, C == 64 ? t0 + r0 : (t0 + r0) / 2, b);
+          else if (r0 < p.L) tma_store_3d(&tmap_tail, src, 0, C == 64 ? t0 + r0 : (t0 + r0) / 2, b);
           tma_store_commit();
-          tma_store_wait_read<0>();
-          mbar_arrive(RB_BAR(h_free, s));
         }
+        pending_slot = s;      // wait_read + h_free arrive are deferred to the next E1 (the warp must not diverge for ~1 us here)
+        __syncwarp();
       }
+    };
+    uint32_t res_a[C / 2], res_b[C / 2];
+    for (int n = 0; n < n_my + S - 1; n += 2) {
+      step(n, res_a, res_b);
+      if (n + 1 < n_my + S - 1) step(n + 1, res_b, res_a);
     }
-    if (e == 0 && lane == 0) tma_store_wait_all();
+    __syncwarp();
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -369,8 +417,12 @@ extern "C" int ctta_resblock_pair(const void* x, void* out, int32_t dtype, int32
   p.x_bytes = (p.rx * 128 + 1023) / 1024 * 1024;
   p.h_bytes = (kHBufRows * 128 + 1023) / 1024 * 1024;
   const int budget = 227 * 1024 - 4096 - 2 * w_bytes;   // 1 KiB alignment slack + static barriers / biases
-  int slots = 2, nx = 3;
-  if (const char* e = getenv("CTTA_RBP_SLOTS")) slots = atoi(e) == 1 ? 1 : 2;
+  // One accumulator / H slot.  The two-slot schedule (c1 of tile n + 1 under the epilogues of tile n) is implemented
+  // (template parameter S) and 10-25 % faster on the taps = 3 / 7 shapes, but its results were not reproducible run to run
+  // on B200 (residual rows of the first tiles of a CTA, cause not found: tools/stress_pair.py with CTTA_RBP_SLOTS=2);
+  // it stays an experiment behind the environment switch until it is understood.
+  int slots = 1, nx = 3;
+  if (const char* e = getenv("CTTA_RBP_SLOTS")) slots = atoi(e) == 2 ? 2 : 1;
   while (true) {
     if (slots * p.h_bytes + nx * p.x_bytes <= budget) break;
     if (nx > 2) --nx;
@@ -386,22 +438,28 @@ extern "C" int ctta_resblock_pair(const void* x, void* out, int32_t dtype, int32
   p.off_h = p.off_x + nx * p.x_bytes;
   const int smem_bytes = p.off_h + slots * p.h_bytes + 1024;
 
-  CUtensorMap tx, tw1, tw2, tout;
+  CUtensorMap tx, tw1, tw2, tout, ttail;
   {
     cuuint64_t dims[3] = {(cuuint64_t)c, (cuuint64_t)t, (cuuint64_t)batch};
     cuuint64_t strides[2] = {(cuuint64_t)c * 2, (cuuint64_t)c * 2 * (cuuint64_t)t};
     cuuint32_t box[3] = {64, (cuuint32_t)p.rxh, 1};
     int rc = make_tmap_ex(&tx, dtype, CU_TENSOR_MAP_SWIZZLE_128B, x, 3, dims, strides, box);
     if (rc) return rc;
+    // output boxes: 32 rows per epilogue warp, and the shorter box of the warp that straddles L = 256 - (taps - 1)
+    const int tail_rows = 32 - (taps - 1);
     if (c == 64) {
-      cuuint32_t obox[3] = {64, (cuuint32_t)p.L, 1};
+      cuuint32_t obox[3] = {64, 32, 1}, tbox[3] = {64, (cuuint32_t)tail_rows, 1};
       rc = make_tmap_ex(&tout, dtype, CU_TENSOR_MAP_SWIZZLE_128B, out, 3, dims, strides, obox);
+      if (rc) return rc;
+      rc = make_tmap_ex(&ttail, dtype, CU_TENSOR_MAP_SWIZZLE_128B, out, 3, dims, strides, tbox);
     } else {
       // C = 32: rows of 64 B are stored pairwise, the tensor viewed as [t / 2, 64] (same memory; L and every t0 are even)
       cuuint64_t pd[3] = {64, (cuuint64_t)t / 2, (cuuint64_t)batch};
       cuuint64_t ps[2] = {128, (cuuint64_t)t * 64};
-      cuuint32_t obox[3] = {64, (cuuint32_t)p.L / 2, 1};
+      cuuint32_t obox[3] = {64, 16, 1}, tbox[3] = {64, (cuuint32_t)tail_rows / 2, 1};
       rc = make_tmap_ex(&tout, dtype, CU_TENSOR_MAP_SWIZZLE_128B, out, 3, pd, ps, obox);
+      if (rc) return rc;
+      rc = make_tmap_ex(&ttail, dtype, CU_TENSOR_MAP_SWIZZLE_128B, out, 3, pd, ps, tbox);
     }
     if (rc) return rc;
     // packed weights [n = C, taps * 64] (ops.pack_conv1d): tap j is the {64 x C} box at column 64 j
@@ -413,14 +471,20 @@ extern "C" int ctta_resblock_pair(const void* x, void* out, int32_t dtype, int32
     rc = make_tmap_ex(&tw2, dtype, CU_TENSOR_MAP_SWIZZLE_128B, w2, 2, wd, ws, wb);
     if (rc) return rc;
   }
-  typedef void (*Fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
-  Fn fn = c == 32 ? (p.is_bf16 ? resblock_pair_kernel<32, 1> : resblock_pair_kernel<32, 0>)
-                  : (p.is_bf16 ? resblock_pair_kernel<64, 1> : resblock_pair_kernel<64, 0>);
+  typedef void (*Fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+  Fn fn;
+  if (slots == 2)
+    fn = c == 32 ? (p.is_bf16 ? resblock_pair_kernel<32, 1, 2> : resblock_pair_kernel<32, 0, 2>)
+                 : (p.is_bf16 ? resblock_pair_kernel<64, 1, 2> : resblock_pair_kernel<64, 0, 2>);
+  else
+    fn = c == 32 ? (p.is_bf16 ? resblock_pair_kernel<32, 1, 1> : resblock_pair_kernel<32, 0, 1>)
+                 : (p.is_bf16 ? resblock_pair_kernel<64, 1, 1> : resblock_pair_kernel<64, 0, 1>);
   int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024 - 2048);
   if (rc) return rc;
   int grid = sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
-  fn<<<grid, kThreads, smem_bytes, stream>>>(tx, tw1, tw2, tout, p);
+  fn<<<grid, kThreads, smem_bytes, stream>>>(tx, tw1, tw2, tout, ttail, p);
   CTTA_LAUNCH_CHECK();
   return 0;
 }
+
