@@ -40,13 +40,13 @@ class PackedModule(nn.Module):
 
     def __init__(self):
         super().__init__()
-        self._pk = None
+        self._pk = {}            # operand dtype -> packed operands (fp16 by default; bf16 when a stage was escalated)
         self._pk_device = None
         self.pack_version = next_pack_version()
         self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module._invalidate())
 
     def _invalidate(self):
-        self._pk = None
+        self._pk = {}
         self._pk_device = None
         self.pack_version = next_pack_version()
 
@@ -63,11 +63,15 @@ class PackedModule(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("%s runs on CUDA only (libctta kernels, no CPU fallback); call .to('cuda') first"
                                % type(self).__name__)
-        if self._pk is None or self._pk_device != dev:
-            with torch.no_grad():
-                self._pk = self._pack({k: v.detach() for k, v in self.state_dict().items()}, dev)
+        from . import ops
+        dt = ops.OPERAND_DTYPE
+        if self._pk_device != dev:
+            self._pk = {}
             self._pk_device = dev
-        return self._pk
+        if dt not in self._pk:   # entries are never replaced: captured graphs hold their pointers
+            with torch.no_grad():
+                self._pk[dt] = self._pack({k: v.detach() for k, v in self.state_dict().items()}, dev)
+        return self._pk[dt]
 
     def to_prepacked(self, device):
         """Moves the module to `device` with the operands packed ON THE HOST first: the packing arithmetic (transposes,
@@ -78,8 +82,9 @@ class PackedModule(nn.Module):
         with torch.no_grad():
             cpu_sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
             pk = self._pack(cpu_sd, torch.device("cpu"))
+        from . import ops
         self.to(device)            # parameters: plain H2D copies; invalidates any previous pack
-        self._pk = tree_to(pk, device)
+        self._pk = {ops.OPERAND_DTYPE: tree_to(pk, device)}
         self._pk_device = next(self.parameters()).device
         return self
 

@@ -16,6 +16,27 @@ from ._lib import (A_CONV1D, A_CONV2D, A_ROWS, ACT_GEGLU, ACT_LRELU, ACT_NONE, A
 # 1e-2 rel-L2 tolerance against the fp32 reference (the reference's own bf16 autocast does not).
 OPERAND_DTYPE = torch.float16
 
+
+class operand_dtype:
+    """Context manager: run a stage with another 16-bit operand type (torch.bfloat16 when fp16's 65504 range overflowed —
+    the reason the reference config carries `upcast_attention`: SD-2.x activations do overflow fp16).  bf16 has fp32's
+    range and 3 fewer mantissa bits; packed operands are kept per dtype (PackedModule.packed)."""
+
+    def __init__(self, dtype):
+        assert dtype in (torch.float16, torch.bfloat16)
+        self.dtype = dtype
+
+    def __enter__(self):
+        global OPERAND_DTYPE
+        self.prev = OPERAND_DTYPE
+        OPERAND_DTYPE = self.dtype
+        return self
+
+    def __exit__(self, *exc):
+        global OPERAND_DTYPE
+        OPERAND_DTYPE = self.prev
+        return False
+
 _DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
 

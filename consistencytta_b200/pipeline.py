@@ -66,6 +66,10 @@ class SingleStepEngine:
         self.text_bucket = max(int(text_bucket), 1)
         self.max_buckets = max(int(max_buckets), 1)
         self.validate_mask = validate_mask
+        # 16-bit operand type per stage: fp16 (what keeps UNet / VAE within the 1e-2 gate) until a stage's output came back
+        # non-finite, then bf16 for that stage from then on (`escalate`; run(check_overflow=True) does it automatically)
+        self.stage_dtype = {"unet": torch.float16, "vae": torch.float16, "vocoder": torch.float16}
+        self.escalations = []
         self._buckets = OrderedDict()
         self._pool = None
         self._versions = None
@@ -77,6 +81,13 @@ class SingleStepEngine:
         """Drops every captured graph and static buffer."""
         self._buckets.clear()
         self.last = None
+
+    def escalate(self, stage):
+        """Switches one stage ('unet' / 'vae' / 'vocoder') to bf16 operands; its buckets are re-created on the next run."""
+        if self.stage_dtype[stage] != torch.bfloat16:
+            self.stage_dtype[stage] = torch.bfloat16
+            self.escalations.append(stage)
+            self.reset()
 
     def _check_versions(self):
         v = (self.unet.pack_version, self.vae.pack_version if self.vae is not None else None)
@@ -91,41 +102,46 @@ class SingleStepEngine:
         cf = guidance_post > 1.0
         # z_N = noise * sigma_max and scale_model_input (consistencytta.py:160,173; heun:151-172) are one device scalar
         x0 = io["x0"]
-        ops.nchw_to_nhwc(io["z"], scale_dev=io["scale"], out=x0[:b])
-        if cf:
-            ops.nchw_to_nhwc(io["z"], scale_dev=io["scale"], out=x0[b:])  # torch.cat([z_n] * 2), consistencytta.py:171
-        if not reuse_text:   # K/V of the prompt for all 16 cross-attention sites: once per prompt set
-            self.unet.project_text(io["enc"], out=io["enc_kv"])
-        lat = self.unet.forward_nhwc(x0, io["t"], io["w"], None, kv_len=io["kv_len"], sample_is_nhwc=True,
-                                     enc_kv=io["enc_kv"])
+        with ops.operand_dtype(self.stage_dtype["unet"]):
+            ops.nchw_to_nhwc(io["z"], scale_dev=io["scale"], out=x0[:b])
+            if cf:
+                ops.nchw_to_nhwc(io["z"], scale_dev=io["scale"], out=x0[b:])  # torch.cat([z_n] * 2), consistencytta.py:171
+            if not reuse_text:   # K/V of the prompt for all 16 cross-attention sites: once per prompt set
+                self.unet.project_text(io["enc"], out=io["enc_kv"])
+            lat = self.unet.forward_nhwc(x0, io["t"], io["w"], None, kv_len=io["kv_len"], sample_is_nhwc=True,
+                                         enc_kv=io["enc_kv"])
         if cf:  # consistencytta.py:182-184
             lat = ops.cfg_mix(lat, float(guidance_post))
         ops.nhwc_to_nchw(lat, out=io["latent"])
         if stages == "unet":
             return
-        mel16 = io["mel16"]
-        mel = self.vae.decode_nhwc(lat, use_ema=use_ema, z_scale=1.0 / float(self.vae.scale_factor), mel16=mel16)
+        mel16 = io["mel16"]      # the vocoder's operand: its dtype is the vocoder stage's
+        with ops.operand_dtype(self.stage_dtype["vae"]):
+            mel = self.vae.decode_nhwc(lat, use_ema=use_ema, z_scale=1.0 / float(self.vae.scale_factor), mel16=mel16)
         refs["mel"] = mel  # fp32 [B,1024,64,1], same memory layout as NCHW [B,1,1024,64]
         if stages == "vae":
             return
-        wav = self.vae.vocoder.forward_btc(mel16.view(b, mel16.shape[1], mel16.shape[2]))
+        with ops.operand_dtype(self.stage_dtype["vocoder"]):
+            wav = self.vae.vocoder.forward_btc(mel16.view(b, mel16.shape[1], mel16.shape[2]))
         refs["wav"] = wav
         ops.wave_to_int16(wav, out=io["i16"])
 
     def _make_io(self, b, n_text, cf, dev):
         bu = 2 * b if cf else b
-        f16 = ops.OPERAND_DTYPE
+        f16 = self.stage_dtype["unet"]
+        with ops.operand_dtype(f16):
+            kv_cols = self.unet.packed()["kv_all"].n
         return {
             "z": torch.zeros((b,) + LATENT_SHAPE, device=dev, dtype=torch.float32),
             "scale": torch.ones(1, device=dev, dtype=torch.float32),
             "x0": torch.zeros(bu, LATENT_SHAPE[1], LATENT_SHAPE[2], LATENT_SHAPE[0], device=dev, dtype=f16),
             "enc": torch.zeros(bu, n_text, 1024, device=dev, dtype=torch.float32),
-            "enc_kv": torch.zeros(bu, n_text, self.unet.packed()["kv_all"].n, device=dev, dtype=f16),
+            "enc_kv": torch.zeros(bu, n_text, kv_cols, device=dev, dtype=f16),
             "kv_len": torch.full((bu,), n_text, device=dev, dtype=torch.int32),
             "t": torch.zeros(bu, device=dev, dtype=torch.float32),
             "w": torch.zeros(bu, device=dev, dtype=torch.float32),
             "latent": torch.zeros((b,) + LATENT_SHAPE, device=dev, dtype=torch.float32),
-            "mel16": torch.zeros(b, 1024, 64, 1, device=dev, dtype=f16),
+            "mel16": torch.zeros(b, 1024, 64, 1, device=dev, dtype=self.stage_dtype["vocoder"]),
             "i16": torch.zeros(b, WAVE_SAMPLES, device=dev, dtype=torch.int16),
         }
 
@@ -179,7 +195,31 @@ class SingleStepEngine:
         return float(t0), float(self.scheduler.init_noise_sigma) * float(self.scheduler.input_scale(t0))
 
     def run(self, noise, enc, mask, guidance, guidance_post=1.0, timestep=None, sigma=None, use_ema=False,
-            stages="all", in_scale=None, reuse_text=False, clone=False):
+            stages="all", in_scale=None, reuse_text=False, clone=False, check_overflow=False):
+        """`_run_once` + the fp16 overflow guard: with check_overflow=True the outputs are tested for inf / NaN (one host
+        synchronisation); the first stage whose output is not finite is escalated to bf16 operands — sticky for this
+        engine — and the request is run again.  fp16's range (65504) is the known weak spot of SD-2.x-style UNets (the
+        reference config carries upcast_attention for it); bf16 trades 3 mantissa bits for fp32's range."""
+        args = (noise, enc, mask, guidance, guidance_post, timestep, sigma, use_ema, stages, in_scale, reuse_text, clone)
+        out = self._run_once(*args)
+        if not check_overflow:
+            return out
+        for _ in range(3):
+            bad = None
+            for stage, key in (("unet", "latent"), ("vae", "mel"), ("vocoder", "wav")):
+                if key in out and not bool(torch.isfinite(out[key]).all()):
+                    bad = stage
+                    break
+            if bad is None or self.stage_dtype[bad] == torch.bfloat16:
+                break
+            if reuse_text:
+                raise RuntimeError("fp16 overflow in a re-query (reuse_text=True): re-run the whole request")
+            self.escalate(bad)
+            out = self._run_once(*args)
+        return out
+
+    def _run_once(self, noise, enc, mask, guidance, guidance_post=1.0, timestep=None, sigma=None, use_ema=False,
+                  stages="all", in_scale=None, reuse_text=False, clone=False):
         """noise [B,8,256,16] fp32 (host or device); enc [B or 2B, L, 1024]; mask bool [B or 2B, L] or None (prefix masks
         only).  The UNet input is `noise * in_scale` at `timestep`; by default the first query of the sampler, N(0,1)
         noise * sigma_max / sqrt(sigma_max^2 + 1) at timesteps[0] (`sigma=` is the Heun shorthand for
@@ -374,6 +414,7 @@ class ConsistencyTTA(TextFrontEnd, nn.Module):
         self.scheduler = scheduler or HeunDiscreteScheduler.from_pretrained(
             pretrained_model_name_or_path="stabilityai/stable-diffusion-2-1", subfolder="scheduler")
         self.engine = SingleStepEngine(self.unet, self.vae, self.scheduler, use_graphs=use_graphs)
+        self.check_overflow = True    # fp16 -> bf16 escalation of a stage whose output came back non-finite (one host sync)
 
     @classmethod
     def from_checkpoints(cls, unet_weight_path="consistencytta_clapft_ckpt/unet_state_dict.pt",
@@ -442,14 +483,23 @@ class ConsistencyTTA(TextFrontEnd, nn.Module):
             later_reuse = False   # micro-batched requests re-project per slice
         else:
             later_reuse = True
-        out = eng.run(noise, enc, mask, cfg_scale_input, cfg_scale_post, t0, in_scale=s0,
-                      stages="unet" if later else "all")
-        for i, t in enumerate(later):
-            zhat = out["latent"]
-            n_i = step_noises[i].to(zhat) if step_noises is not None else torch.randn_like(zhat)
-            zn = sched.add_noise(zhat, n_i, t)
-            out = eng.run(zn, enc, mask, cfg_scale_input, cfg_scale_post, float(t), in_scale=sched.input_scale(t),
-                          stages="all" if i == len(later) - 1 else "unet", reuse_text=later_reuse)
+        for attempt in range(4):
+            out = eng.run(noise, enc, mask, cfg_scale_input, cfg_scale_post, t0, in_scale=s0,
+                          stages="unet" if later else "all", check_overflow=self.check_overflow)
+            for i, t in enumerate(later):
+                zhat = out["latent"]
+                n_i = step_noises[i].to(zhat) if step_noises is not None else torch.randn_like(zhat)
+                zn = sched.add_noise(zhat, n_i, t)
+                out = eng.run(zn, enc, mask, cfg_scale_input, cfg_scale_post, float(t), in_scale=sched.input_scale(t),
+                              stages="all" if i == len(later) - 1 else "unet", reuse_text=later_reuse)
+            if not (self.check_overflow and later):
+                break
+            # a re-query cannot escalate by itself (its prompt K/V belong to the old operand type): test the final outputs
+            bad = next((st for st, key in (("unet", "latent"), ("vae", "mel"), ("vocoder", "wav"))
+                        if key in out and not bool(torch.isfinite(out[key]).all())), None)
+            if bad is None or eng.stage_dtype[bad] == torch.bfloat16:
+                break
+            eng.escalate(bad)
         out = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in out.items()}   # engine buffers are reused
         return out if return_all else out["int16"]
 

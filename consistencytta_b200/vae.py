@@ -354,7 +354,7 @@ class AutoencoderKL(nn.Module):
         mod = self.post_quant_conv
         if use_ema and self.ema_post_quant_conv is not None:
             mod = self.ema_post_quant_conv
-        key = ("ema" if mod is self.ema_post_quant_conv else "raw", float(z_scale), str(mod.weight.device))
+        key = ("ema" if mod is self.ema_post_quant_conv else "raw", float(z_scale), str(mod.weight.device), ops.OPERAND_DTYPE)
         if key not in self._pq:   # one entry per key, kept alive: captured graphs hold the pointer
             self._pq[key] = ops.pack_conv2d(mod.weight.detach().float() * float(z_scale), mod.bias.detach())
         return self._pq[key]
