@@ -20,6 +20,7 @@ ap.add_argument("--w", type=int, default=16)
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--kind", default="c1", choices=["c1", "c2", "c2h", "f32res", "f16", "geglu"])
 ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--stats", action="store_true", help="also emit the fused GroupNorm moments of the result (32 groups)")
 ap.add_argument("--seconds", type=float, default=0.0, help="sustained mode: repeat for this long first (power-capped clocks)")
 a = ap.parse_args()
 dev = "cuda"
@@ -55,6 +56,10 @@ elif a.kind == "f32res":
     kw = dict(out=torch.empty(shape, device=dev), residual=torch.randn(shape, device=dev))
 else:
     kw = dict(out=torch.empty(shape, device=dev, dtype=DT))
+if a.stats:
+    kw.update(stats=torch.empty(a.batch, 32, 2, device=dev), stats_groups=32)
+    if a.what == "linear":
+        kw.update(stats_rows_per_img=a.rows // a.batch)
 for _ in range(a.iters):
     fn(x, pw, **kw)
 torch.cuda.synchronize()
@@ -73,5 +78,5 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
 rows = x.numel() // a.c
-print("%s c=%d n=%d taps=%d rows=%d kind=%s: %.3f ms  %.1f TFLOP/s" % (a.what, a.c, n, pw.ntaps, rows, a.kind, ms,
+print("%s c=%d n=%d taps=%d rows=%d kind=%s%s: %.3f ms  %.1f TFLOP/s" % (a.what, a.c, n, pw.ntaps, rows, a.kind, "+stats" if a.stats else "", ms,
       2.0 * rows * n * pw.ntaps * a.c / ms / 1e9))
