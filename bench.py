@@ -392,7 +392,8 @@ def main():
                        "parallelism": "dp%d (prompts sharded by batch, no collective on the hot path)" % world,
                        "cuda_graph": True},
             "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "output": ("every rank's int16 clips gathered to rank 0 (NCCL gather, side stream) and copied to pinned "
+                    "output": ("latents copied to pinned host memory" if args.unet_only else
+                               "every rank's int16 clips gathered to rank 0 (NCCL gather, side stream) and copied to pinned "
                                "host memory there" if gat is not None else "int16 clips copied to pinned host memory")},
             "gpu_launches": int(var.get("launches") or 0) * args.steps,
             "clocks": clocks,
