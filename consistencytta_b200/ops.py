@@ -166,6 +166,45 @@ def pack_conv1d(weight, bias=None, dilation=1, dtype=None):
     return PackedWeight(_pack_taps(w_ntc, dtype), _bias(bias, cout, w.device), k, cin, cout, d0, [0] * k)
 
 
+def pack_conv1d_folded(weight, bias, fold, dtype=None):
+    """nn.Conv1d weight [cout, cin, k] (stride 1, dilation 1, 'same' padding) for the FOLDED view of the sequence:
+    `fold` consecutive time steps form one GEMM row, x[B, T, cin] read as [B, T / fold, fold * cin] (the same memory) and
+    y[B, T, cout] written as [B, T / fold, fold * cout].  Output sub-position g of folded row m needs input time
+    fold*m + g + s (s = j - (k-1)/2) = fold*(m + r) + f, so kernel tap j = fold*r + f - g + (k-1)/2 lands in folded tap r,
+    input block f, output block g of a block-Toeplitz weight [fold*cout, taps', fold*cin] (zero where j falls outside
+    [0, k)).  Exact (zeros are added), and the conv's zero padding in time is the folded conv's zero padding in rows.
+    Why: the narrow HiFi-GAN stages (C = 32 / 64) are bound by the tcgen05.mma issue floor (~60 cycles per instruction at
+    N <= 64, whatever N and K are); folding to N = K-chunk = 128 does 2-4x the useful work per instruction with 3-5 folded
+    taps instead of 3-11.  T must be a multiple of `fold`."""
+    dtype = dtype or OPERAND_DTYPE
+    w = weight.detach().float()
+    cout, cin, k = w.shape
+    p = (k - 1) // 2
+    r_lo = (0 - p - (fold - 1)) // fold          # floor((g + s - f) / fold) over s in [-p, p], g, f in [0, fold)
+    r_hi = (fold - 1 + p) // fold
+    taps = []
+    for r in range(r_lo, r_hi + 1):
+        blk = torch.zeros(fold, cout, fold, cin, device=w.device)
+        for g in range(fold):
+            for f in range(fold):
+                j = fold * r + f - g + p
+                if 0 <= j < k:
+                    blk[g, :, f, :] = w[:, :, j]
+        taps.append(blk.reshape(fold * cout, fold * cin))
+    # drop all-zero outer taps (possible when fold does not divide the reach evenly)
+    while len(taps) > 1 and not taps[0].any():
+        taps.pop(0)
+        r_lo += 1
+    while len(taps) > 1 and not taps[-1].any():
+        taps.pop()
+        r_hi -= 1
+    w_ntc = torch.stack(taps, dim=1).contiguous()                      # [fold*cout, taps', fold*cin]
+    b = None if bias is None else bias.detach().float().repeat(fold)
+    ntaps = len(taps)
+    return PackedWeight(_pack_taps(w_ntc, dtype), _bias(b, fold * cout, w.device), ntaps, fold * cin, fold * cout,
+                        list(range(r_lo, r_hi + 1)), [0] * ntaps)
+
+
 def pack_conv_transpose1d(weight, bias, stride, padding, dtype=None):
     """nn.ConvTranspose1d weight [cin, cout, k] -> one PackedWeight per output phase r in [0, stride).
 

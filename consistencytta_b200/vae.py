@@ -50,9 +50,33 @@ class Generator(PackedModule):
                                                                  sd["resblocks.%d.convs1.%d.bias" % (n, m)], dilation=d)
                     pk["rb.%d.c2.%d" % (n, m)] = ops.pack_conv1d(sd["resblocks.%d.convs2.%d.weight" % (n, m)],
                                                                  sd["resblocks.%d.convs2.%d.bias" % (n, m)], dilation=1)
+                    # narrow stages: dilation-1 convs also in the time-folded form (ops.pack_conv1d_folded)
+                    ch = sd["resblocks.%d.convs2.%d.weight" % (n, m)].shape[0]
+                    fold = self.fold_factor(ch, ks)
+                    if fold > 1:
+                        pk["rb.%d.c2.%d.fold" % (n, m)] = ops.pack_conv1d_folded(
+                            sd["resblocks.%d.convs2.%d.weight" % (n, m)], sd["resblocks.%d.convs2.%d.bias" % (n, m)], fold)
+                        if d == 1:
+                            pk["rb.%d.c1.%d.fold" % (n, m)] = ops.pack_conv1d_folded(
+                                sd["resblocks.%d.convs1.%d.weight" % (n, m)], sd["resblocks.%d.convs1.%d.bias" % (n, m)], fold)
         # one output channel: pointwise GEMM over the 7 taps + shifted sum (ops.single_channel_conv)
         pk["conv_post"] = ops.pack_single_channel_conv(sd["conv_post.weight"], sd["conv_post.bias"])
         return pk
+
+    @staticmethod
+    def fold_factor(ch, ks):
+        """Time steps folded into one GEMM row for a dilation-1 conv of `ch` channels and `ks` taps (1 = not folded):
+        C = 32 -> 4 (N = K-chunk = 128, 3 / 3 / 5 folded taps for k = 3 / 7 / 11), C = 64 -> 2 for k <= 7 (3 / 5 folded
+        taps; k = 11 would need 7 and measures slower).  OPT-IN (CTTA_FOLD=1): exact and 15-25 % faster per launch in the
+        eager profile, but the captured pipeline measures the same clips/s (369.4 vs 369.1, profiles/r2_fold.txt) — the
+        folded problems run like the C = 128 stage, which is bound by its 16-bit epilogue / TMA rows, not by the MMA floor."""
+        if os.environ.get("CTTA_FOLD") is None:
+            return 1
+        if ch == 32:
+            return 4
+        if ch == 64 and ks <= 7:
+            return 2
+        return 1
 
     def out_length(self, t):
         for u, k in zip(self.h["upsample_rates"], self.h["upsample_kernel_sizes"]):
@@ -96,10 +120,24 @@ class Generator(PackedModule):
                         ops.resblock_pair(cur, pw1, pw2, slope, out=dst)
                         cur = dst
                         continue
-                    ops.conv1d(cur, pw1, out2=tmp16, act2=ACT_LRELU, act2_slope=slope)
+                    f1, f2 = pk.get("rb.%d.c1.%d.fold" % (n, m)), pk.get("rb.%d.c2.%d.fold" % (n, m))
+                    fold = (f2.n // c) if f2 is not None else 1
+                    if fold > 1 and t % fold != 0:
+                        f1 = f2 = None
+
+                    def fv(x):   # [B, T, C] read as [B, T / fold, fold * C]: the same memory
+                        return x.view(b, t // fold, fold * c)
+                    if f1 is not None:
+                        ops.conv1d(fv(cur), f1, out2=fv(tmp16), act2=ACT_LRELU, act2_slope=slope)
+                    else:
+                        ops.conv1d(cur, pw1, out2=tmp16, act2=ACT_LRELU, act2_slope=slope)
                     # x' = x + c2(lrelu(c1(lrelu(x)))) with x recovered from lrelu(x); emitted again as lrelu(x')
-                    ops.conv1d(tmp16, pk["rb.%d.c2.%d" % (n, m)], residual=cur, res_neg_scale=1.0 / slope, out2=dst,
-                               act2=ACT_LRELU, act2_slope=slope)
+                    if f2 is not None:
+                        ops.conv1d(fv(tmp16), f2, residual=fv(cur), res_neg_scale=1.0 / slope, out2=fv(dst),
+                                   act2=ACT_LRELU, act2_slope=slope)
+                    else:
+                        ops.conv1d(tmp16, pw2, residual=cur, res_neg_scale=1.0 / slope, out2=dst,
+                                   act2=ACT_LRELU, act2_slope=slope)
                     cur = dst
             # x = (sum_j resblock_j(x)) / 3 (models.py:108-112), then LeakyReLU of models.py:104 / :113 (default slope)
             cur16 = ops.mrf_combine(branch, slope, 1.0 / nk, 0.01 if last else 0.1, out=tmp16)

@@ -209,6 +209,38 @@ def test_resblock_pair_fused(c, k, dil, t, bsz):
     assert rel(out, two) < 1e-3
 
 
+@pytest.mark.parametrize("c,k,fold,t,bsz", [(32, 3, 4, 1000, 2), (32, 7, 4, 4096, 3), (32, 11, 4, 163872, 2), (64, 3, 2, 81936, 2),
+                                            (64, 7, 2, 2502, 3), (32, 11, 2, 64, 1), (64, 11, 2, 300, 2)])
+def test_conv1d_time_folded(c, k, fold, t, bsz):
+    """Dilation-1 HiFi-GAN convs in the time-folded form (ops.pack_conv1d_folded): `fold` time steps per GEMM row and a
+    block-Toeplitz weight — same result as F.conv1d with 'same' zero padding (hifigan/models.py:16-17,59,61), on the
+    LeakyReLU'ed 16-bit stream with the residual epilogue of the ResBlock."""
+    torch.manual_seed(17)
+    slope = 0.1
+    x = torch.randn(bsz, t, c, device=DEV)
+    lx = F.leaky_relu(x, slope).to(DT)
+    a = r16(torch.randn(bsz, t, c, device=DEV))
+    wt = r16(torch.randn(c, c, k, device=DEV) / math.sqrt(k * c))
+    b = torch.randn(c, device=DEV)
+    pw = ops.pack_conv1d_folded(wt, b, fold)
+    assert pw.n == fold * c and pw.c == fold * c and pw.ntaps <= (k + 2 * fold - 2) // fold + 1
+    out2 = torch.empty(bsz, t, c, device=DEV, dtype=DT)
+
+    def fv(z):
+        return z.view(bsz, t // fold, fold * c)
+    ops.conv1d(fv(a.to(DT)), pw, residual=fv(lx), res_neg_scale=1.0 / slope, out2=fv(out2), act2=ops.ACT_LRELU,
+               act2_slope=slope)
+    lxf = lx.float()
+    x_rec = torch.where(lxf < 0, lxf / slope, lxf)
+    ref = F.conv1d(a.permute(0, 2, 1), wt, b, padding=(k - 1) // 2).permute(0, 2, 1) + x_rec
+    assert rel(out2, F.leaky_relu(ref, slope)) < 1e-3
+    # and against the unfolded kernel path
+    direct = torch.empty_like(out2)
+    ops.conv1d(a.to(DT), ops.pack_conv1d(wt, b), residual=lx, res_neg_scale=1.0 / slope, out2=direct, act2=ops.ACT_LRELU,
+               act2_slope=slope)
+    assert rel(out2, direct) < 1e-3
+
+
 def test_resblock_pair_unsupported_shapes_are_refused():
     assert not ops.resblock_pair_supported(64, 11, 1)        # resident weights of both convs exceed shared memory
     assert not ops.resblock_pair_supported(128, 3, 1) and not ops.resblock_pair_supported(32, 4, 1) and not ops.resblock_pair_supported(32, 3, 1, 1001)
