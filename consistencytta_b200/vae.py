@@ -162,6 +162,9 @@ class Decoder(PackedModule):
             raise ValueError("only the audioldm-s-full first-stage decoder is implemented")
         sch = {k[len("decoder."):]: v for k, v in weights.vae_decoder_schema(cfg).items() if k.startswith("decoder.")}
         register_tree(self, sch)
+        # levels whose residual stream is held in the 16-bit operand type (0 = 128 ch at 1024 x 64, 1 = 256 ch at 512 x 32):
+        # there the stream IS the HBM traffic (fp32: 2.1 / 1.1 GB per tensor at B = 64).  CTTA_VAE_STREAM16=0: all fp32.
+        self.stream16_levels = () if os.environ.get("CTTA_VAE_STREAM16") == "0" else (0, 1)
 
     def _pack(self, sd, dev):
         pk = {}
@@ -180,9 +183,11 @@ class Decoder(PackedModule):
                     pk[name] = (w.float().contiguous(), sd[name + ".bias"].float().contiguous())
         return pk
 
-    def _resnet(self, pk, p, x, x_stats):
+    def _resnet(self, pk, p, x, x_stats, stream16=False):
         """ResnetBlock.forward (temb None), modules.py:155-175.  x_stats: GroupNorm moments of x emitted by the kernel
-        that wrote x.  Returns (out, moments of out)."""
+        that wrote x.  Returns (out, moments of out).  `stream16`: the block's output (the residual stream) is written in
+        the 16-bit operand type instead of fp32 — used at the two high-resolution levels, where the stream is the HBM
+        traffic (x may arrive in either type; the accumulation itself stays fp32 in the epilogue)."""
         b, h, w, cin = x.shape
         dev = x.device
         has_sc = (p + ".nin_shortcut") in pk
@@ -196,12 +201,13 @@ class Decoder(PackedModule):
         del a
         a2 = ops.groupnorm_apply(hid, GROUPS, st2, *pk[p + ".norm2"], eps=EPS, act=ACT_SILU)
         del hid
+        sdt = ops.OPERAND_DTYPE if stream16 else torch.float32
         if has_sc:
-            res = torch.empty(b, h, w, cout, device=dev, dtype=torch.float32)
+            res = torch.empty(b, h, w, cout, device=dev, dtype=sdt)
             ops.conv2d(raw, pk[p + ".nin_shortcut"], out=res)
         else:
             res = x
-        out = torch.empty(b, h, w, cout, device=dev, dtype=torch.float32)
+        out = torch.empty(b, h, w, cout, device=dev, dtype=sdt)
         out_stats = torch.empty(b, GROUPS, 2, device=dev, dtype=torch.float32)
         ops.conv2d(a2, pk[p + ".conv2"], out=out, residual=res, stats=out_stats, stats_groups=GROUPS)
         return out, out_stats
@@ -255,11 +261,11 @@ class Decoder(PackedModule):
         x, st = self._resnet(pk, "mid.block_2", x, st)
         for lvl in (2, 1, 0):
             for blk in range(3):
-                x, st = self._resnet(pk, "up.%d.block.%d" % (lvl, blk), x, st)
+                x, st = self._resnet(pk, "up.%d.block.%d" % (lvl, blk), x, st, stream16=lvl in self.stream16_levels)
             if lvl != 0:  # Upsample, modules.py:53-57
                 bb, hh, ww, cc = x.shape
                 # nearest 2x + conv3x3 as four 2x2 phase convs on the low-resolution tensor (4/9 of the FLOPs)
-                x16 = ops.groupnorm_apply(x, 1, None, None, None, act=ACT_NONE)
+                x16 = x if x.dtype != torch.float32 else ops.groupnorm_apply(x, 1, None, None, None, act=ACT_NONE)
                 del x
                 x = torch.empty(bb, 2 * hh, 2 * ww, cc, device=dev, dtype=torch.float32)
                 st = torch.empty(b, GROUPS, 2, device=dev, dtype=torch.float32)
