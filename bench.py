@@ -82,7 +82,7 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
@@ -91,6 +91,7 @@ class ClockSampler:
             try:
                 sm.append(float(parts[1]))
                 mx.append(float(parts[2]))
+                pw.append(float(parts[3]))
             except ValueError:
                 continue
             for nm, v in zip(names, parts[4:8]):
@@ -101,7 +102,7 @@ class ClockSampler:
         except OSError:
             pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def cpu_reference_clips_per_s(text_len, steps, warmup, threads=None, batch=1, inputs=None, guidance=4.0):
