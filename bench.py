@@ -91,9 +91,12 @@ class ClockSampler:
             try:
                 sm.append(float(parts[1]))
                 mx.append(float(parts[2]))
-                pw.append(float(parts[3]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(parts[3]))
+            except ValueError:
+                pass
             for nm, v in zip(names, parts[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
