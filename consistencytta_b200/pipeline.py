@@ -240,6 +240,12 @@ class SingleStepEngine:
             timestep = t0 if timestep is None else timestep
             in_scale = s0 if in_scale is None else in_scale
         b = noise.shape[0]
+        if b == 0 or enc.shape[1] == 0:
+            raise ValueError("empty request: need at least one clip and one text token (got %d clips, %d tokens)"
+                             % (b, enc.shape[1]))
+        if tuple(noise.shape[1:]) != LATENT_SHAPE or enc.shape[2] != 1024:
+            raise ValueError("noise must be [B, 8, 256, 16] and text embeddings [B, L, 1024], got %s / %s"
+                             % (tuple(noise.shape), tuple(enc.shape)))
         if self.max_batch and b > self.max_batch:
             return self._run_micro_batches(noise, enc, mask, guidance, guidance_post, timestep, in_scale, use_ema,
                                            stages, reuse_text)
