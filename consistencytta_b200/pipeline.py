@@ -35,6 +35,17 @@ def slice_request_rows(t, lo, hi, b, cf):
     return t[lo:hi]
 
 
+def scheduler_input_scale(scheduler, timestep):
+    """The scalar `scheduler.scale_model_input(x, t)` multiplies x by.  Our schedulers expose it as `input_scale`; for any
+    other object with the diffusers scheduler surface (e.g. the reference's own HeunDiscreteScheduler / DDIMScheduler
+    passed to `AudioLCM.inference`) it is read off a probe tensor."""
+    if hasattr(scheduler, "input_scale"):
+        return float(scheduler.input_scale(timestep))
+    probe = torch.ones(1, 1, 1, 1)
+    t = timestep if torch.is_tensor(timestep) else torch.tensor(timestep)
+    return float(scheduler.scale_model_input(probe, t).reshape(-1)[0])
+
+
 class SingleStepEngine:
     """The hot path: scheduler prologue -> UNet -> (post-CFG) -> VAE decode -> HiFi-GAN -> centring / int16.
 
@@ -192,7 +203,7 @@ class SingleStepEngine:
         model is queried at first (consistencytta.py:159-160,186; audio_consistency_model.py:489-496)."""
         self.scheduler.set_timesteps(18)
         t0 = self.scheduler.timesteps[0]
-        return float(t0), float(self.scheduler.init_noise_sigma) * float(self.scheduler.input_scale(t0))
+        return float(t0), float(self.scheduler.init_noise_sigma) * scheduler_input_scale(self.scheduler, t0)
 
     def run(self, noise, enc, mask, guidance, guidance_post=1.0, timestep=None, sigma=None, use_ema=False,
             stages="all", in_scale=None, reuse_text=False, clone=False, check_overflow=False):
@@ -496,7 +507,7 @@ class ConsistencyTTA(TextFrontEnd, nn.Module):
                 zhat = out["latent"]
                 n_i = step_noises[i].to(zhat) if step_noises is not None else torch.randn_like(zhat)
                 zn = sched.add_noise(zhat, n_i, t)
-                out = eng.run(zn, enc, mask, cfg_scale_input, cfg_scale_post, float(t), in_scale=sched.input_scale(t),
+                out = eng.run(zn, enc, mask, cfg_scale_input, cfg_scale_post, float(t), in_scale=scheduler_input_scale(sched, t),
                               stages="all" if i == len(later) - 1 else "unet", reuse_text=later_reuse)
             if not (self.check_overflow and later):
                 break
@@ -590,7 +601,7 @@ class AudioLCM(TextFrontEnd, nn.Module):
             n_i = step_noises[i].to(zhat) if step_noises is not None else torch.randn_like(zhat)
             zn = inference_scheduler.add_noise(zhat, n_i, t)
             out = eng.run(zn, enc, mask, guidance_scale_input, guidance_scale_post, float(t),
-                          in_scale=inference_scheduler.input_scale(t), stages="unet", reuse_text=reuse)
+                          in_scale=scheduler_input_scale(inference_scheduler, t), stages="unet", reuse_text=reuse)
         return out["latent"].clone()
 
     @torch.no_grad()

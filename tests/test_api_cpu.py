@@ -294,3 +294,26 @@ def test_engine_text_bucket_and_lru_bookkeeping():
     assert len(eng._buckets) == 2 and (4, 48, False, "cuda:0") not in eng._buckets and c is not a
     with pytest.raises(RuntimeError):
         eng.run(torch.zeros(1, 8, 256, 16), torch.zeros(1, 4, 1024), None, 3.0)   # CPU models: no fallback
+
+
+def test_scheduler_input_scale_works_for_foreign_scheduler_objects():
+    """AudioLCM.inference(prompt, inference_scheduler, ...) may be handed the reference's own scheduler object, which has
+    no `input_scale`: the factor is then read off `scale_model_input` with a probe tensor."""
+    from consistencytta_b200 import DDIMScheduler, HeunDiscreteScheduler
+    from consistencytta_b200.pipeline import scheduler_input_scale
+
+    class Foreign:                       # diffusers surface only
+        def __init__(self, inner):
+            self._s = inner
+
+        def scale_model_input(self, sample, timestep):
+            return self._s.scale_model_input(sample, timestep)
+
+    h = HeunDiscreteScheduler.from_pretrained()
+    h.set_timesteps(18)
+    for t in (h.timesteps[0], h.timesteps[5]):
+        assert abs(scheduler_input_scale(Foreign(h), t) - h.input_scale(t)) < 1e-7
+        assert abs(scheduler_input_scale(h, t) - h.input_scale(t)) == 0
+    d = DDIMScheduler.from_pretrained()
+    d.set_timesteps(18)
+    assert scheduler_input_scale(Foreign(d), d.timesteps[0]) == 1.0
