@@ -13,10 +13,12 @@
 //   c1  acc1[m] += X[rows m*128 + j*d ...] . W1[j]      tap j = a row-shifted UMMA view of the resident box
 //   E1  h = lrelu(acc1 + b1) (0 outside [0, T): c2's zero padding) -> 16-bit K-major SW128 tile H in shared memory
 //   c2  acc2[m] += H[rows m*128 + j ...] . W2[j]
-//   E2  lrelu(acc2 + b2 + x) with x = un-lrelu(lx) read back from the X box -> 16-bit staging tile -> TMA store of L rows
+//   E2  lrelu(acc2 + b2 + x) with x = un-lrelu(lx) re-read from global memory (L2 hits) -> 16-bit staging tile -> TMA store
+//       of L rows
 // All taps of W1 and W2 stay resident in shared memory for the whole (persistent) CTA.  Warp roles: warp 0 = TMA
-// loader (X ring), warp 1 = single-thread tcgen05.mma issuer, warps 2..9 = epilogue (thread == row of one 128-row tile).
-// Tiles run through S "slots" (accumulators + H buffer) so that c1 of tile n + 1 runs under the epilogues of tile n.
+// loader (X ring), warp 1 = single-thread tcgen05.mma issuer, warps 2..9 = E1, warps 10..17 = E2 (thread == row of one
+// 128-row tile in both).  Tiles run through S "slots" (accumulators + H buffer), so that c1 of tile n + 1, E1 of tile
+// n + 1 and E2 of tile n overlap.
 //
 // These stages are bound by the ~60-cycle issue floor of tcgen05.mma at N <= 64 (profiles/r1_umma_rate_microbench.txt),
 // not by HBM: the fusion removes the second launch's epilogue / HBM round trip, the MMA count stays.
@@ -32,8 +34,9 @@ int make_tmap_ex(CUtensorMap* m, int dtype, CUtensorMapSwizzle swz, const void* 
 
 namespace rbp {
 
-constexpr int kThreads = 320;          // 10 warps
-constexpr int kEpiWarp0 = 2;           // warps 2..9
+constexpr int kThreads = 576;          // 18 warps
+constexpr int kEpiWarp0 = 2;           // warps 2..9: E1 (hidden tile)
+constexpr int kEpi2Warp0 = 10;         // warps 10..17: E2 (output tile)
 constexpr int kHRows = 256;            // hidden rows per tile (two UMMA M tiles)
 constexpr int kHBufRows = 272;         // H buffer: the second M tile's taps read up to 10 rows past 256
 constexpr int kMaxX = 4, kMaxSlots = 2;
@@ -47,6 +50,7 @@ struct Params {
   int off_w1, off_w2, off_x, x_bytes, off_h, h_bytes;
   const float* b1;
   const float* b2;
+  const void* x;                       // the input tensor itself: residual rows are re-read from global memory (an L2 hit)
   float slope, inv_slope;
   int is_bf16;
 };
@@ -76,7 +80,32 @@ __device__ __forceinline__ void unpack2(uint32_t v, float& a, float& b) {
     b = f.y;
   }
 }
-__device__ __forceinline__ float lrelu(float v, float slope) { return v >= 0.f ? v : v * slope; }
+// Packed fp32 pairs (FADD2 / FMUL2 on sm_100): IEEE round-to-nearest like the scalar forms, half the issue slots — the
+// epilogue warps are issue / latency bound (two E1 + two E2 warps per scheduler).
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  uint64_t a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+// v > 0 ? v : s * v  ==  max(v, s v) for s in (0, 1],  min(v, s v) for s > 1 (the inverse map)
+template <bool kInverse>
+__device__ __forceinline__ void lrelu2(float& v0, float& v1, float s) {
+  uint64_t a, b;
+  float m0, m1;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(v0), "f"(v1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(s));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(m0), "=f"(m1) : "l"(a));
+  if (kInverse) {
+    v0 = fminf(v0, m0);
+    v1 = fminf(v1, m1);
+  } else {
+    v0 = fmaxf(v0, m0);
+    v1 = fmaxf(v1, m1);
+  }
+}
 
 template <int C, int BF16, int S>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -87,7 +116,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   constexpr int NCH = C / 8;            // 16-byte chunks per row
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) Bars bars_s;
-  __shared__ float bias_s[2][64];
+  __shared__ __align__(16) float bias_s[2][64];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -101,7 +130,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     mbar_init(RB_BAR(w_full, 0), 1);
     for (int i = 0; i < kMaxX; ++i) {
       mbar_init(RB_BAR(x_full, i), 1);
-      mbar_init(RB_BAR(x_empty, i), 8);        // the 8 epilogue warps, once c1 has completed and their residual rows are in registers
+      mbar_init(RB_BAR(x_empty, i), 1);        // tcgen05.commit of the issuer, once c1 has consumed the box
     }
     for (int i = 0; i < kMaxSlots; ++i) {
       mbar_init(RB_BAR(acc1_full, i), 1);
@@ -176,6 +205,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             }
           }
           umma_commit(RB_BAR(acc1_full, s));
+          umma_commit(RB_BAR(x_empty, dx));      // the box goes back to the loader as soon as these MMAs have read it
         }
         const int i2 = n - (S - 1);
         if (i2 >= 0 && i2 < n_my) {
@@ -201,157 +231,153 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue warps: thread == row of one 128-row tile
+  } else if (warp < kEpi2Warp0) {
+    // ------------------------------------------------------------------ E1 warps: thread == row of one 128-row hidden tile
+    //   h = lrelu(c1 + b1), zero outside the sequence (c2's zero padding) -> K-major SW128 tile H(s)
     const int e = warp - kEpiWarp0;
     const int m = e >> 2;                           // which of the two 128-row tiles
     const int q = warp & 3;                         // TMEM lane quarter this warp may touch
-    const int row = q * 32 + lane;
-    const int hr = m * 128 + row;                   // row of the 256-row hidden / output tile
+    const int hr = m * 128 + q * 32 + lane;         // row of the 256-row hidden tile
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const float slope = p.slope;
+    for (int n = 0; n < n_my; ++n) {
+      const int s = n % S;
+      const int tile = blockIdx.x + n * gridDim.x;
+      const int b = tile / p.tiles_per_seq, t0 = (tile - b * p.tiles_per_seq) * p.L;
+      mbar_wait(RB_BAR(acc1_full, s), static_cast<uint32_t>((n / S) & 1));
+      tc_fence_after();
+      __syncwarp();          // tcgen05.ld is warp-collective (.sync.aligned): reconverge after the divergent wait loop
+      uint32_t u[C];
+      const uint32_t a1 = tmem_base + lane_addr + static_cast<uint32_t>(s * 4 * C + m * C);
+      tmem_ld_x32(a1, u);
+      if (C == 64) tmem_ld_x32(a1 + 32, u + (C == 64 ? 32 : 0));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(RB_BAR(acc1_free, s));
+      const int th = t0 - p.p2 + hr;
+      const bool valid = th >= 0 && th < p.T;
+      mbar_wait(RB_BAR(h_free, s), static_cast<uint32_t>(((n / S) & 1) ^ 1));   // every E2 warp's store out of this buffer has read it
+      const uint32_t h_row = base + p.off_h + s * p.h_bytes + static_cast<uint32_t>(hr) * 128u;
+      const uint32_t xr = static_cast<uint32_t>(hr & 7);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const float4 ba = *reinterpret_cast<const float4*>(&bias_s[0][8 * ch]);
+        const float4 bb = *reinterpret_cast<const float4*>(&bias_s[0][8 * ch + 4]);
+        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = 8 * ch + 2 * i;
+          float v0 = __uint_as_float(u[c0]), v1 = __uint_as_float(u[c0 + 1]);
+          add2(v0, v1, bv[2 * i], bv[2 * i + 1]);
+          lrelu2<false>(v0, v1, slope);
+          w[i] = valid ? pack2<BF16>(v0, v1) : 0u;
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_row + ((static_cast<uint32_t>(ch) ^ xr) << 4)),
+                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(RB_BAR(h_full, s));
+    }
+  } else {
+    // ------------------------------------------------------------------ E2 warps: thread == row of one 128-row output tile
+    //   lrelu(c2 + b2 + x), x recovered from the lrelu'ed input -> 16-bit staging rows (in H(s), which c2 has consumed) ->
+    //   per-warp TMA stores.  A separate warp set from E1, so that E1 of tile n + 1 and E2 of tile n run side by side.
+    const int e = warp - kEpi2Warp0;
+    const int m = e >> 2;
+    const int q = warp & 3;
+    const int hr = m * 128 + q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const float slope = p.slope, inv_slope = p.inv_slope;
-    // One step of the epilogue schedule: E1 of tile n (if any), then E2 of tile n - (S - 1) (if any).  The residual rows of
-    // a tile are pulled out of its X box into registers during E1 (`res_new`), so the box goes back to the loader as soon
-    // as c1 has consumed it instead of being held until E2; with S = 2 the E2 of a step belongs to the PREVIOUS tile, whose
-    // rows are in the other register set (`res_old`) — hence the two-step unrolled loop below.
     int pending_slot = -1;   // slot whose staging rows this warp's last TMA store may still be reading
-    auto step = [&](int n, uint32_t (&res_new)[C / 2], uint32_t (&res_old)[C / 2]) {
-      if (n < n_my) {
-        // ---- E1: h = lrelu(c1 + b1), zero outside the sequence, -> K-major SW128 tile
-        const int s = n % S, dx = n % NX;
-        const int tile = blockIdx.x + n * gridDim.x;
-        const int b = tile / p.tiles_per_seq, t0 = (tile - b * p.tiles_per_seq) * p.L;
-        mbar_wait(RB_BAR(acc1_full, s), static_cast<uint32_t>((n / S) & 1));
-        tc_fence_after();
-        __syncwarp();          // tcgen05.ld is warp-collective (.sync.aligned): reconverge after the divergent wait loop
-        uint32_t u[C];
-        const uint32_t a1 = tmem_base + lane_addr + static_cast<uint32_t>(s * 4 * C + m * C);
-        tmem_ld_x32(a1, u);
-        if (C == 64) tmem_ld_x32(a1 + 32, u + (C == 64 ? 32 : 0));
-        // residual rows (lrelu'ed input of output row hr = X row hr + p2 + p1) while the TMEM load is in flight.
-        // The box was written by the TMA unit (async proxy): a thread that reads it with ordinary loads has to observe the
-        // box's own mbarrier ITSELF — knowing through acc1_full that the issuer saw it complete is not enough (without this
-        // wait, rows of the box came back with the contents of an earlier launch).  The phase has completed long ago.
-        mbar_wait(RB_BAR(x_full, dx), static_cast<uint32_t>((n / NX) & 1));
-        {
-          const int xrow = hr + p.p2 + p.p1;
-          const uint32_t x_row = base + p.off_x + dx * p.x_bytes + static_cast<uint32_t>(xrow) * 128u;
-          const uint32_t xx = static_cast<uint32_t>(xrow & 7);
+    for (int n = 0; n < n_my; ++n) {
+      const int s = n % S;
+      const int tile = blockIdx.x + n * gridDim.x;
+      const int b = tile / p.tiles_per_seq, t0 = (tile - b * p.tiles_per_seq) * p.L;
+      // residual rows (the lrelu'ed input at the output row's own time step) straight from global memory, issued before
+      // anything is waited for: the X box holding the same rows was fetched a moment ago, so these are L2 hits whose
+      // latency hides under the c2 wait.  (Reading them back from the X box with ld.shared was not reliable against the
+      // TMA unit refilling the ring.)  Rows >= L belong to the next tile.
+      uint32_t res[C / 2];
+      {
+        const int tr = t0 + hr;
+        if (hr < p.L && tr < p.T) {
+          const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.x) +
+                                                            (static_cast<size_t>(b) * p.T + tr) * (2u * C));
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch)
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(res_new[4 * ch]), "=r"(res_new[4 * ch + 1]), "=r"(res_new[4 * ch + 2]), "=r"(res_new[4 * ch + 3])
-                         : "r"(x_row + ((static_cast<uint32_t>(ch) ^ xx) << 4))
-                         : "memory");
-        }
-        tmem_ld_wait();
-        // The box is handed back below, and the loader's next TMA write may follow within a microsecond.  An issued
-        // ld.shared is NOT a completed one: the arrive was observed to overtake loads still queued in the memory pipeline
-        // (the residual of tile n then came from tile n + NX).  Instructions that CONSUME the loaded registers cannot issue
-        // before the data is back, and the warp issues in order — so the arrive's ADDRESS is made to depend on a fold of them.
-        uint32_t dep;
-        {
-          uint32_t f = 0;
+          for (int ch = 0; ch < NCH; ++ch) {
+            const uint4 v = __ldg(src + ch);
+            res[4 * ch] = v.x;
+            res[4 * ch + 1] = v.y;
+            res[4 * ch + 2] = v.z;
+            res[4 * ch + 3] = v.w;
+          }
+        } else {
 #pragma unroll
-          for (int i = 0; i < C / 2; ++i) f ^= res_new[i];
-          f = __reduce_or_sync(0xffffffffu, f);                         // every lane's loads
-          asm volatile("and.b32 %0, %1, 0;" : "=r"(dep) : "r"(f));      // opaque 0 that depends on them
+          for (int i = 0; i < C / 2; ++i) res[i] = 0u;
         }
-        tc_fence_before();
-        __syncwarp();
+      }
+      // hand back the staging rows of this warp's previous TMA store BEFORE waiting for c2: with one slot, c2 of this tile
+      // cannot start until E1 has rewritten the buffer, which waits for exactly this arrive
+      if (pending_slot >= 0) {
         if (lane == 0) {
-          mbar_arrive(RB_BAR(acc1_free, s));
-          mbar_arrive(RB_BAR(x_empty, dx) + dep);      // c1 has completed (acc1_full) and this warp has its residual rows
+          tma_store_wait_read<0>();
+          mbar_arrive(RB_BAR(h_free, pending_slot));
         }
-        const int th = t0 - p.p2 + hr;
-        const bool valid = th >= 0 && th < p.T;
-        // hand back the staging rows of this warp's previous TMA store: by now (one TMEM load later) it has read them
-        if (pending_slot >= 0) {
-          if (lane == 0) {
-            tma_store_wait_read<0>();
-            mbar_arrive(RB_BAR(h_free, pending_slot));
-          }
-          pending_slot = -1;
-          __syncwarp();
-        }
-        mbar_wait(RB_BAR(h_free, s), static_cast<uint32_t>(((n / S) & 1) ^ 1));   // every warp's store out of this buffer has read it
-        const uint32_t h_row = base + p.off_h + s * p.h_bytes + static_cast<uint32_t>(hr) * 128u;
-        const uint32_t xr = static_cast<uint32_t>(hr & 7);
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          uint32_t w[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c0 = 8 * ch + 2 * i;
-            const float v0 = valid ? lrelu(__uint_as_float(u[c0]) + bias_s[0][c0], slope) : 0.f;
-            const float v1 = valid ? lrelu(__uint_as_float(u[c0 + 1]) + bias_s[0][c0 + 1], slope) : 0.f;
-            w[i] = pack2<BF16>(v0, v1);
-          }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_row + ((static_cast<uint32_t>(ch) ^ xr) << 4)),
-                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(RB_BAR(h_full, s));
-      }
-      const int i2 = n - (S - 1);
-      if (i2 >= 0 && i2 < n_my) {
-        // ---- E2: lrelu(c2 + b2 + x), x recovered from the lrelu'ed input rows held in registers since E1
-        uint32_t (&res)[C / 2] = *(S == 2 ? &res_old : &res_new);
-        const int s = i2 % S;
-        const int tile = blockIdx.x + i2 * gridDim.x;
-        const int b = tile / p.tiles_per_seq, t0 = (tile - b * p.tiles_per_seq) * p.L;
-        mbar_wait(RB_BAR(acc2_full, s), static_cast<uint32_t>((i2 / S) & 1));
-        tc_fence_after();
-        __syncwarp();
-        uint32_t u[C];
-        const uint32_t a2 = tmem_base + lane_addr + static_cast<uint32_t>(s * 4 * C + 2 * C + m * C);
-        tmem_ld_x32(a2, u);
-        if (C == 64) tmem_ld_x32(a2 + 32, u + (C == 64 ? 32 : 0));
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(RB_BAR(acc2_free, s));
-        // staging tile: dense rows of 2 C bytes, SW128 on the linear address (what the TMA store un-swizzles)
-        const uint32_t st_base = base + p.off_h + s * p.h_bytes;
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          uint32_t w[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c0 = 8 * ch + 2 * i;
-            float x0, x1;
-            unpack2<BF16>(res[4 * ch + i], x0, x1);
-            x0 = x0 >= 0.f ? x0 : x0 * inv_slope;
-            x1 = x1 >= 0.f ? x1 : x1 * inv_slope;
-            const float v0 = lrelu(__uint_as_float(u[c0]) + bias_s[1][c0] + x0, slope);
-            const float v1 = lrelu(__uint_as_float(u[c0 + 1]) + bias_s[1][c0 + 1] + x1, slope);
-            w[i] = pack2<BF16>(v0, v1);
-          }
-          const uint32_t lin = static_cast<uint32_t>(hr) * (2u * C) + static_cast<uint32_t>(ch) * 16u;
-          const uint32_t phys = lin ^ (((lin >> 7) & 7u) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_base + phys), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-                       "r"(w[3]) : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-        // every warp stores its own 32 rows (no CTA-wide rendezvous): rows >= L belong to the next tile, so the warp that
-        // straddles L uses the shorter box and the ones past it store nothing; rows past the end of the sequence are clipped
-        if (lane == 0) {     // always the same thread: bulk async-groups are per thread (wait_read / wait_all)
-          const int r0 = m * 128 + q * 32;
-          const uint32_t src = st_base + static_cast<uint32_t>(r0) * (2u * C);
-          if (r0 + 32 <= p.L) tma_store_3d(&tmap_out, src, 0, C == 64 ? t0 + r0 : (t0 + r0) / 2, b);
-          else if (r0 < p.L) tma_store_3d(&tmap_tail, src, 0, C == 64 ? t0 + r0 : (t0 + r0) / 2, b);
-          tma_store_commit();
-        }
-        pending_slot = s;      // wait_read + h_free arrive are deferred to the next E1 (the warp must not diverge for ~1 us here)
+        pending_slot = -1;
         __syncwarp();
       }
-    };
-    uint32_t res_a[C / 2], res_b[C / 2];
-    for (int n = 0; n < n_my + S - 1; n += 2) {
-      step(n, res_a, res_b);
-      if (n + 1 < n_my + S - 1) step(n + 1, res_b, res_a);
+      mbar_wait(RB_BAR(acc2_full, s), static_cast<uint32_t>((n / S) & 1));
+      tc_fence_after();
+      __syncwarp();
+      uint32_t u[C];
+      const uint32_t a2 = tmem_base + lane_addr + static_cast<uint32_t>(s * 4 * C + 2 * C + m * C);
+      tmem_ld_x32(a2, u);
+      if (C == 64) tmem_ld_x32(a2 + 32, u + (C == 64 ? 32 : 0));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(RB_BAR(acc2_free, s));
+      // staging tile: dense rows of 2 C bytes, SW128 on the linear address (what the TMA store un-swizzles)
+      const uint32_t st_base = base + p.off_h + s * p.h_bytes;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const float4 ba = *reinterpret_cast<const float4*>(&bias_s[1][8 * ch]);
+        const float4 bb = *reinterpret_cast<const float4*>(&bias_s[1][8 * ch + 4]);
+        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = 8 * ch + 2 * i;
+          float x0, x1;
+          unpack2<BF16>(res[4 * ch + i], x0, x1);
+          lrelu2<true>(x0, x1, inv_slope);               // x from lrelu(x)
+          float v0 = __uint_as_float(u[c0]), v1 = __uint_as_float(u[c0 + 1]);
+          add2(v0, v1, bv[2 * i], bv[2 * i + 1]);
+          add2(v0, v1, x0, x1);
+          lrelu2<false>(v0, v1, slope);
+          w[i] = pack2<BF16>(v0, v1);
+        }
+        const uint32_t lin = static_cast<uint32_t>(hr) * (2u * C) + static_cast<uint32_t>(ch) * 16u;
+        const uint32_t phys = lin ^ (((lin >> 7) & 7u) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_base + phys), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                     "r"(w[3]) : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      // every warp stores its own 32 rows (no CTA-wide rendezvous): rows >= L belong to the next tile, so the warp that
+      // straddles L uses the shorter box and the ones past it store nothing; rows past the end of the sequence are clipped
+      if (lane == 0) {     // always the same thread: bulk async-groups are per thread (wait_read / wait_all)
+        const int r0 = m * 128 + q * 32;
+        const uint32_t src = st_base + static_cast<uint32_t>(r0) * (2u * C);
+        if (r0 + 32 <= p.L) tma_store_3d(&tmap_out, src, 0, C == 64 ? t0 + r0 : (t0 + r0) / 2, b);
+        else if (r0 < p.L) tma_store_3d(&tmap_tail, src, 0, C == 64 ? t0 + r0 : (t0 + r0) / 2, b);
+        tma_store_commit();
+      }
+      pending_slot = s;
+      __syncwarp();
     }
     __syncwarp();
     if (lane == 0) tma_store_wait_all();
@@ -409,6 +435,7 @@ extern "C" int ctta_resblock_pair(const void* x, void* out, int32_t dtype, int32
   p.w_tap_bytes = c * 128;
   p.b1 = b1;
   p.b2 = b2;
+  p.x = x;
   p.slope = slope;
   p.inv_slope = 1.f / slope;
   p.is_bf16 = dtype == CTTA_BF16;
@@ -417,19 +444,17 @@ extern "C" int ctta_resblock_pair(const void* x, void* out, int32_t dtype, int32
   p.x_bytes = (p.rx * 128 + 1023) / 1024 * 1024;
   p.h_bytes = (kHBufRows * 128 + 1023) / 1024 * 1024;
   const int budget = 227 * 1024 - 4096 - 2 * w_bytes;   // 1 KiB alignment slack + static barriers / biases
-  // One accumulator / H slot.  The two-slot schedule (c1 of tile n + 1 under the epilogues of tile n) is implemented
-  // (template parameter S) and 10-25 % faster on the taps = 3 / 7 shapes, but its results were not reproducible run to run
-  // on B200 (residual rows of the first tiles of a CTA, cause not found: tools/stress_pair.py with CTTA_RBP_SLOTS=2);
-  // it stays an experiment behind the environment switch until it is understood.
-  int slots = 1, nx = 3;
-  if (const char* e = getenv("CTTA_RBP_SLOTS")) slots = atoi(e) == 2 ? 2 : 1;
+  // Two accumulator / H slots where shared memory allows (c1 + E1 of tile n + 1 under c2 + E2 of tile n), else one.
+  // CTTA_RBP_SLOTS=1 forces the one-slot schedule (A/B switch).
+  int slots = 2, nx = 3;
+  if (const char* e = getenv("CTTA_RBP_SLOTS")) slots = atoi(e) == 1 ? 1 : 2;
+  // a one-deep X "ring" is enough with two slots: the box of tile n + 1 lands while the issuer runs c2 of tile n - 1
   while (true) {
     if (slots * p.h_bytes + nx * p.x_bytes <= budget) break;
-    if (nx > 2) --nx;
+    if (nx > (slots == 2 ? 1 : 2)) --nx;
     else if (slots > 1) { slots = 1; nx = 3; }
     else return set_error(CTTA_ERR_UNSUPPORTED, "resblock_pair: shared memory plan does not fit");
   }
-  if (slots * 4 * c > 512) slots = 1;
   p.n_slots = slots;
   p.n_x = nx;
   p.off_w1 = 0;

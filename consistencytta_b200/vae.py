@@ -28,10 +28,10 @@ class Generator(PackedModule):
             self.h.update({k: h[k] for k in weights.HIFIGAN_CONFIG if k in h})
         self.num_kernels = len(self.h["resblock_kernel_sizes"])
         self.num_upsamples = len(self.h["upsample_rates"])
-        # Fused ResBlock-pair kernel on the C <= 64 stages (ctta_resblock_pair) instead of two ctta_gemm launches per pair.
-        # OFF by default: it halves the HBM traffic of those stages, but they are bound by the tcgen05.mma issue floor at
-        # N <= 64 and by epilogue latency, not by HBM — measured equal to the unfused path (profiles/r2_resblock_pair.txt).
-        self.fuse_pairs = os.environ.get("CTTA_FUSE_PAIRS") is not None
+        # Fused ResBlock-pair kernel on the C <= 64 stages (ctta_resblock_pair) instead of two ctta_gemm launches per pair:
+        # bit-identical output, 9-40 % less time per pair (profiles/r2_resblock_pair.txt).  CTTA_FUSE_PAIRS=0 switches back
+        # to the two-launch path (A/B runs).
+        self.fuse_pairs = os.environ.get("CTTA_FUSE_PAIRS", "1") not in ("", "0")
         register_tree(self, weights.vocoder_schema(self.h, prefix=""))
 
     def remove_weight_norm(self):
