@@ -23,6 +23,7 @@
 // These stages are bound by the ~60-cycle issue floor of tcgen05.mma at N <= 64 (profiles/r1_umma_rate_microbench.txt),
 // not by HBM: the fusion removes the second launch's epilogue / HBM round trip, the MMA count stays.
 #include <cuda.h>
+#include <cstdio>
 #include <cstdlib>
 #include "ctta_internal.h"
 #include "ctta_ptx.cuh"
@@ -48,12 +49,29 @@ struct Params {
   int n_x, n_slots;                    // X ring depth, accumulator / H slots
   int w_tap_bytes;                     // C * 128
   int off_w1, off_w2, off_x, x_bytes, off_h, h_bytes;
+  int off_st, n_st;                    // own output staging buffers (0 = the output rows are staged in H(s))
   const float* b1;
   const float* b2;
+  long long* trace;                    // RBP_TRACE builds only (tools/trace_pair.py): clock64 stamps of CTA 0, else null
   const void* x;                       // the input tensor itself: residual rows are re-read from global memory (an L2 hit)
   float slope, inv_slope;
   int is_bf16;
 };
+
+// Phase stamps of CTA 0 (20 slots per tile) for tools/trace_pair.py; compiled out of the product library.
+#ifndef RBP_TRACE
+#define RBP_TRACE 0
+#endif
+#if RBP_TRACE
+#define RBP_STAMP(ev, n)                                                                   \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && (n) < 48 && p.trace) p.trace[(n) * 20 + (ev)] = clock64();      \
+  } while (0)
+#else
+#define RBP_STAMP(ev, n) \
+  do {                   \
+  } while (0)
+#endif
 
 struct Bars {
   uint64_t w_full, x_full[kMaxX], x_empty[kMaxX], acc1_full[kMaxSlots], acc1_free[kMaxSlots], h_full[kMaxSlots],
@@ -136,7 +154,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       mbar_init(RB_BAR(acc1_full, i), 1);
       mbar_init(RB_BAR(acc1_free, i), 8);
       mbar_init(RB_BAR(h_full, i), 8);
-      mbar_init(RB_BAR(h_free, i), 8);         // every epilogue warp, once its TMA store has read its staging rows
+      mbar_init(RB_BAR(h_free, i), p.n_st == 0 ? 8 : 1);   // shared staging: every E2 warp, once its TMA store has read its rows; else the issuer's commit after c2
       mbar_init(RB_BAR(acc2_full, i), 1);
       mbar_init(RB_BAR(acc2_free, i), 8);
     }
@@ -170,6 +188,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const int dx = n % NX;
         mbar_wait(RB_BAR(x_empty, dx), static_cast<uint32_t>(((n / NX) & 1) ^ 1));
         const uint32_t full = RB_BAR(x_full, dx);
+        RBP_STAMP(0, n);
         mbar_arrive_expect_tx(full, static_cast<uint32_t>(p.rx) * 128u);
         const uint32_t dst = base + p.off_x + dx * p.x_bytes;
         const int r0 = t0 - p.p2 - p.p1;          // negative / past-the-end rows are zero filled by the TMA unit
@@ -191,6 +210,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           mbar_wait(RB_BAR(x_full, dx), static_cast<uint32_t>((n / NX) & 1));
           mbar_wait(RB_BAR(acc1_free, s), static_cast<uint32_t>(((n / S) & 1) ^ 1));
           tc_fence_after();
+          RBP_STAMP(1, n);
           const uint32_t x_lo = umma_desc_lo(base + p.off_x + dx * p.x_bytes);
 #pragma unroll 1
           for (int m = 0; m < 2; ++m) {
@@ -204,6 +224,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 umma_f16(d_tmem, umma_desc_from_lo(a_lo + 2 * kk), umma_desc_from_lo(b_lo + 2 * kk), idesc, (j | kk) != 0 ? 1u : 0u);
             }
           }
+          RBP_STAMP(2, n);
           umma_commit(RB_BAR(acc1_full, s));
           umma_commit(RB_BAR(x_empty, dx));      // the box goes back to the loader as soon as these MMAs have read it
         }
@@ -214,6 +235,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           mbar_wait(RB_BAR(h_full, s), static_cast<uint32_t>((i2 / S) & 1));
           mbar_wait(RB_BAR(acc2_free, s), static_cast<uint32_t>(((i2 / S) & 1) ^ 1));
           tc_fence_after();
+          RBP_STAMP(3, i2);
           const uint32_t h_lo = umma_desc_lo(base + p.off_h + s * p.h_bytes);
 #pragma unroll 1
           for (int m = 0; m < 2; ++m) {
@@ -227,7 +249,9 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 umma_f16(d_tmem, umma_desc_from_lo(a_lo + 2 * kk), umma_desc_from_lo(b_lo + 2 * kk), idesc, (j | kk) != 0 ? 1u : 0u);
             }
           }
+          RBP_STAMP(4, i2);
           umma_commit(RB_BAR(acc2_full, s));
+          if (p.n_st != 0) umma_commit(RB_BAR(h_free, s));      // own staging buffers: H(s) is free once c2 has read it
         }
       }
     }
@@ -247,39 +271,58 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       mbar_wait(RB_BAR(acc1_full, s), static_cast<uint32_t>((n / S) & 1));
       tc_fence_after();
       __syncwarp();          // tcgen05.ld is warp-collective (.sync.aligned): reconverge after the divergent wait loop
-      uint32_t u[C];
+      if (warp == kEpiWarp0 && lane == 0) RBP_STAMP(5, n);
       const uint32_t a1 = tmem_base + lane_addr + static_cast<uint32_t>(s * 4 * C + m * C);
-      tmem_ld_x32(a1, u);
-      if (C == 64) tmem_ld_x32(a1 + 32, u + (C == 64 ? 32 : 0));
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(RB_BAR(acc1_free, s));
       const int th = t0 - p.p2 + hr;
       const bool valid = th >= 0 && th < p.T;
-      mbar_wait(RB_BAR(h_free, s), static_cast<uint32_t>(((n / S) & 1) ^ 1));   // every E2 warp's store out of this buffer has read it
       const uint32_t h_row = base + p.off_h + s * p.h_bytes + static_cast<uint32_t>(hr) * 128u;
       const uint32_t xr = static_cast<uint32_t>(hr & 7);
+      // 32 columns at a time (C = 64: two passes): 32 accumulator + 32 bias registers live, no spills; the bias loads are
+      // issued with the tensor-memory load, so one shared-memory latency per pass instead of one per 8 columns
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        const float4 ba = *reinterpret_cast<const float4*>(&bias_s[0][8 * ch]);
-        const float4 bb = *reinterpret_cast<const float4*>(&bias_s[0][8 * ch + 4]);
-        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-        uint32_t w[4];
+      for (int hf = 0; hf < C / 32; ++hf) {
+        float bv[32];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c0 = 8 * ch + 2 * i;
-          float v0 = __uint_as_float(u[c0]), v1 = __uint_as_float(u[c0 + 1]);
-          add2(v0, v1, bv[2 * i], bv[2 * i + 1]);
-          lrelu2<false>(v0, v1, slope);
-          w[i] = valid ? pack2<BF16>(v0, v1) : 0u;
+        for (int i = 0; i < 8; ++i) {
+          const float4 t4 = *reinterpret_cast<const float4*>(&bias_s[0][32 * hf + 4 * i]);
+          bv[4 * i] = t4.x;
+          bv[4 * i + 1] = t4.y;
+          bv[4 * i + 2] = t4.z;
+          bv[4 * i + 3] = t4.w;
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_row + ((static_cast<uint32_t>(ch) ^ xr) << 4)),
-                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        uint32_t u[32];
+        tmem_ld_x32(a1 + 32 * hf, u);
+        tmem_ld_wait();
+        if (hf == C / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(RB_BAR(acc1_free, s));
+          if (warp == kEpiWarp0 && lane == 0) RBP_STAMP(6, n);
+        }
+        if (hf == 0) {
+          mbar_wait(RB_BAR(h_free, s), static_cast<uint32_t>(((n / S) & 1) ^ 1));   // every E2 warp's store out of this buffer has read it
+          if (warp == kEpiWarp0 && lane == 0) RBP_STAMP(7, n);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c0 = 8 * ch + 2 * i;
+            float v0 = __uint_as_float(u[c0]), v1 = __uint_as_float(u[c0 + 1]);
+            add2(v0, v1, bv[c0], bv[c0 + 1]);
+            lrelu2<false>(v0, v1, slope);
+            w[i] = valid ? pack2<BF16>(v0, v1) : 0u;
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_row + ((static_cast<uint32_t>(4 * hf + ch) ^ xr) << 4)),
+                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
+        }
       }
+      if (warp == kEpiWarp0 && lane == 0) RBP_STAMP(15, n);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(RB_BAR(h_full, s));
+      if (warp == kEpiWarp0 && lane == 0) RBP_STAMP(8, n);
     }
   } else {
     // ------------------------------------------------------------------ E2 warps: thread == row of one 128-row output tile
@@ -300,6 +343,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       // anything is waited for: the X box holding the same rows was fetched a moment ago, so these are L2 hits whose
       // latency hides under the c2 wait.  (Reading them back from the X box with ld.shared was not reliable against the
       // TMA unit refilling the ring.)  Rows >= L belong to the next tile.
+      if (warp == kEpi2Warp0 && lane == 0) RBP_STAMP(9, n);
       uint32_t res[C / 2];
       {
         const int tr = t0 + hr;
@@ -319,57 +363,84 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           for (int i = 0; i < C / 2; ++i) res[i] = 0u;
         }
       }
-      // hand back the staging rows of this warp's previous TMA store BEFORE waiting for c2: with one slot, c2 of this tile
-      // cannot start until E1 has rewritten the buffer, which waits for exactly this arrive
-      if (pending_slot >= 0) {
-        if (lane == 0) {
+      if (warp == kEpi2Warp0 && lane == 0) RBP_STAMP(17, n);
+      // Shared staging (the output rows are staged in H(s), p.n_st == 0): hand back the rows of this warp's previous TMA
+      // store — wait until it has READ them, then h_free — BEFORE waiting for c2: with one slot, c2 of this tile cannot
+      // start until E1 has rewritten the buffer, which waits for exactly this arrive.
+      if (p.n_st == 0 && pending_slot >= 0) {
+        if (elect_one_sync()) {
           tma_store_wait_read<0>();
           mbar_arrive(RB_BAR(h_free, pending_slot));
         }
         pending_slot = -1;
         __syncwarp();
       }
+      if (warp == kEpi2Warp0 && lane == 0) RBP_STAMP(10, n);
       mbar_wait(RB_BAR(acc2_full, s), static_cast<uint32_t>((n / S) & 1));
       tc_fence_after();
       __syncwarp();
-      uint32_t u[C];
+      if (warp == kEpi2Warp0 && lane == 0) RBP_STAMP(11, n);
       const uint32_t a2 = tmem_base + lane_addr + static_cast<uint32_t>(s * 4 * C + 2 * C + m * C);
-      tmem_ld_x32(a2, u);
-      if (C == 64) tmem_ld_x32(a2 + 32, u + (C == 64 ? 32 : 0));
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(RB_BAR(acc2_free, s));
-      // staging tile: dense rows of 2 C bytes, SW128 on the linear address (what the TMA store un-swizzles)
-      const uint32_t st_base = base + p.off_h + s * p.h_bytes;
+      // staging tile: dense rows of 2 C bytes, SW128 on the linear address (what the TMA store un-swizzles).  Own buffers
+      // (p.n_st = 1 / 2, each warp re-uses only its own rows) where shared memory allows: E1 of tile n + S then waits for
+      // c2 of tile n alone (h_free committed by the issuer), not for this warp set's TMA stores.
+      const uint32_t st_base = p.n_st == 0 ? base + p.off_h + s * p.h_bytes
+                                           : base + p.off_st + (p.n_st == 2 ? (n & 1) : 0) * (256 * 2 * C);
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        const float4 ba = *reinterpret_cast<const float4*>(&bias_s[1][8 * ch]);
-        const float4 bb = *reinterpret_cast<const float4*>(&bias_s[1][8 * ch + 4]);
-        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-        uint32_t w[4];
+      for (int hf = 0; hf < C / 32; ++hf) {
+        float bv[32];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c0 = 8 * ch + 2 * i;
-          float x0, x1;
-          unpack2<BF16>(res[4 * ch + i], x0, x1);
-          lrelu2<true>(x0, x1, inv_slope);               // x from lrelu(x)
-          float v0 = __uint_as_float(u[c0]), v1 = __uint_as_float(u[c0 + 1]);
-          add2(v0, v1, bv[2 * i], bv[2 * i + 1]);
-          add2(v0, v1, x0, x1);
-          lrelu2<false>(v0, v1, slope);
-          w[i] = pack2<BF16>(v0, v1);
+        for (int i = 0; i < 8; ++i) {
+          const float4 t4 = *reinterpret_cast<const float4*>(&bias_s[1][32 * hf + 4 * i]);
+          bv[4 * i] = t4.x;
+          bv[4 * i + 1] = t4.y;
+          bv[4 * i + 2] = t4.z;
+          bv[4 * i + 3] = t4.w;
         }
-        const uint32_t lin = static_cast<uint32_t>(hr) * (2u * C) + static_cast<uint32_t>(ch) * 16u;
-        const uint32_t phys = lin ^ (((lin >> 7) & 7u) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_base + phys), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-                     "r"(w[3]) : "memory");
+        uint32_t u[32];
+        tmem_ld_x32(a2 + 32 * hf, u);
+        tmem_ld_wait();
+        if (hf == C / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(RB_BAR(acc2_free, s));
+          if (warp == kEpi2Warp0 && lane == 0) RBP_STAMP(12, n);
+        }
+        if (hf == 0 && p.n_st != 0) {      // this warp's store out of the rows it is about to overwrite has read them
+          if (elect_one_sync()) {
+            if (p.n_st == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c0 = 8 * ch + 2 * i;
+            float x0, x1;
+            unpack2<BF16>(res[16 * hf + 4 * ch + i], x0, x1);
+            lrelu2<true>(x0, x1, inv_slope);               // x from lrelu(x)
+            float v0 = __uint_as_float(u[c0]), v1 = __uint_as_float(u[c0 + 1]);
+            add2(v0, v1, bv[c0], bv[c0 + 1]);
+            add2(v0, v1, x0, x1);
+            lrelu2<false>(v0, v1, slope);
+            w[i] = pack2<BF16>(v0, v1);
+          }
+          const uint32_t lin = static_cast<uint32_t>(hr) * (2u * C) + static_cast<uint32_t>(4 * hf + ch) * 16u;
+          const uint32_t phys = lin ^ (((lin >> 7) & 7u) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_base + phys), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                       "r"(w[3]));
+        }
       }
+      if (warp == kEpi2Warp0 && lane == 0) RBP_STAMP(16, n);
       fence_proxy_async();
       __syncwarp();
+      if (warp == kEpi2Warp0 && lane == 0) RBP_STAMP(13, n);
       // every warp stores its own 32 rows (no CTA-wide rendezvous): rows >= L belong to the next tile, so the warp that
       // straddles L uses the shorter box and the ones past it store nothing; rows past the end of the sequence are clipped
-      if (lane == 0) {     // always the same thread: bulk async-groups are per thread (wait_read / wait_all)
+      if (elect_one_sync()) {     // the same thread every time (full mask): bulk async-groups are per thread (wait_read / wait_all)
         const int r0 = m * 128 + q * 32;
         const uint32_t src = st_base + static_cast<uint32_t>(r0) * (2u * C);
         if (r0 + 32 <= p.L) tma_store_3d(&tmap_out, src, 0, C == 64 ? t0 + r0 : (t0 + r0) / 2, b);
@@ -378,9 +449,10 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       }
       pending_slot = s;
       __syncwarp();
+      if (warp == kEpi2Warp0 && lane == 0) RBP_STAMP(14, n);
     }
     __syncwarp();
-    if (lane == 0) tma_store_wait_all();
+    if (elect_one_sync()) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -436,6 +508,10 @@ extern "C" int ctta_resblock_pair(const void* x, void* out, int32_t dtype, int32
   p.b1 = b1;
   p.b2 = b2;
   p.x = x;
+  p.trace = nullptr;
+#if RBP_TRACE
+  if (const char* e = getenv("CTTA_RBP_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+#endif
   p.slope = slope;
   p.inv_slope = 1.f / slope;
   p.is_bf16 = dtype == CTTA_BF16;
@@ -444,24 +520,43 @@ extern "C" int ctta_resblock_pair(const void* x, void* out, int32_t dtype, int32
   p.x_bytes = (p.rx * 128 + 1023) / 1024 * 1024;
   p.h_bytes = (kHBufRows * 128 + 1023) / 1024 * 1024;
   const int budget = 227 * 1024 - 4096 - 2 * w_bytes;   // 1 KiB alignment slack + static barriers / biases
-  // Two accumulator / H slots where shared memory allows (c1 + E1 of tile n + 1 under c2 + E2 of tile n), else one.
-  // CTTA_RBP_SLOTS=1 forces the one-slot schedule (A/B switch).
-  int slots = 2, nx = 3;
+  // Shared-memory plan, in order of preference (CTTA_RBP_SLOTS=1 / CTTA_RBP_STAGING=0|1|2 force a variant for A/B runs):
+  // two accumulator / H slots (c1 + E1 of tile n + 1 under c2 + E2 of tile n) with own output staging buffers (two, then
+  // one), then with the output staged in H(s); X ring 3 -> 1 deep (one box is enough with two slots: the box of tile
+  // n + 1 lands while the issuer runs c2 of tile n - 1); last, one slot.
+  int slots = 2, nx = 3, n_st = 2;
   if (const char* e = getenv("CTTA_RBP_SLOTS")) slots = atoi(e) == 1 ? 1 : 2;
-  // a one-deep X "ring" is enough with two slots: the box of tile n + 1 lands while the issuer runs c2 of tile n - 1
-  while (true) {
-    if (slots * p.h_bytes + nx * p.x_bytes <= budget) break;
-    if (nx > (slots == 2 ? 1 : 2)) --nx;
-    else if (slots > 1) { slots = 1; nx = 3; }
-    else return set_error(CTTA_ERR_UNSUPPORTED, "resblock_pair: shared memory plan does not fit");
+  int st_max = 2;
+  if (const char* e = getenv("CTTA_RBP_STAGING")) st_max = atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e));
+  const int st_bytes = 256 * 2 * c;
+  int x_max = 3;
+  if (const char* e = getenv("CTTA_RBP_X")) x_max = atoi(e) < 1 ? 1 : (atoi(e) > 3 ? 3 : atoi(e));
+  bool ok = false;
+  for (int pass = 0; pass < 2 && !ok; ++pass) {
+    const int sl = pass == 0 ? slots : 1;
+    // a two-deep X ring matters more than the staging buffers (measured), so: x >= 2 with staging 2, 1, 0, then x = 1
+    for (int x_min = 2; x_min >= (sl == 2 ? 1 : 2) && !ok; --x_min)
+      for (int st = st_max; st >= 0 && !ok; --st)
+        for (int x = x_max; x >= x_min && !ok; --x)
+          if (sl * p.h_bytes + x * p.x_bytes + st * st_bytes <= budget) {
+            slots = sl;
+            nx = x;
+            n_st = st;
+            ok = true;
+          }
   }
+  if (!ok) return set_error(CTTA_ERR_UNSUPPORTED, "resblock_pair: shared memory plan does not fit");
   p.n_slots = slots;
   p.n_x = nx;
+  p.n_st = n_st;
   p.off_w1 = 0;
   p.off_w2 = w_bytes;
   p.off_x = 2 * w_bytes;
   p.off_h = p.off_x + nx * p.x_bytes;
-  const int smem_bytes = p.off_h + slots * p.h_bytes + 1024;
+  p.off_st = p.off_h + slots * p.h_bytes;
+  const int smem_bytes = p.off_st + n_st * st_bytes + 1024;
+  if (getenv("CTTA_DEBUG") != nullptr)
+    fprintf(stderr, "ctta_resblock_pair: c=%d taps=%d dil=%d slots=%d x=%d staging=%d smem=%d\n", c, taps, dilation, slots, nx, n_st, smem_bytes);
 
   CUtensorMap tx, tw1, tw2, tout, ttail;
   {
