@@ -49,6 +49,7 @@ struct Params {
   int n_x, n_slots;                    // X ring depth, accumulator / H slots
   int w_tap_bytes;                     // C * 128
   int off_w1, off_w2, off_x, x_bytes, off_h, h_bytes;
+  int x_al32;                          // x is 32-byte aligned: residual rows by 256-bit loads
   int off_st, n_st;                    // own output staging buffers (0 = the output rows are staged in H(s))
   const float* b1;
   const float* b2;
@@ -350,13 +351,24 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         if (hr < p.L && tr < p.T) {
           const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.x) +
                                                             (static_cast<size_t>(b) * p.T + tr) * (2u * C));
+          if (p.x_al32) {
+            // 256-bit loads (LDG.E.256): a row is 128 B away from the next lane's, so every load instruction touches 32
+            // (C = 64) / 16 (C = 32) distinct lines and the L1 tag stage is the limit — half the instructions, half the lookups
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) {
-            const uint4 v = __ldg(src + ch);
-            res[4 * ch] = v.x;
-            res[4 * ch + 1] = v.y;
-            res[4 * ch + 2] = v.z;
-            res[4 * ch + 3] = v.w;
+            for (int ch = 0; ch < NCH; ch += 2)
+              asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                           : "=r"(res[4 * ch]), "=r"(res[4 * ch + 1]), "=r"(res[4 * ch + 2]), "=r"(res[4 * ch + 3]),
+                             "=r"(res[4 * ch + 4]), "=r"(res[4 * ch + 5]), "=r"(res[4 * ch + 6]), "=r"(res[4 * ch + 7])
+                           : "l"(src + ch));
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+              const uint4 v = __ldg(src + ch);
+              res[4 * ch] = v.x;
+              res[4 * ch + 1] = v.y;
+              res[4 * ch + 2] = v.z;
+              res[4 * ch + 3] = v.w;
+            }
           }
         } else {
 #pragma unroll
@@ -508,6 +520,7 @@ extern "C" int ctta_resblock_pair(const void* x, void* out, int32_t dtype, int32
   p.b1 = b1;
   p.b2 = b2;
   p.x = x;
+  p.x_al32 = (reinterpret_cast<uintptr_t>(x) & 31) == 0 ? 1 : 0;
   p.trace = nullptr;
 #if RBP_TRACE
   if (const char* e = getenv("CTTA_RBP_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));

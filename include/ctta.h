@@ -216,7 +216,9 @@ int ctta_lrelu_cast(const float* x, int64_t numel, float slope, void* y, int32_t
  * [batch, t, c]; w1 / w2 are K-major packed weights [c, taps * 64] (taps of 64 zero-padded input channels each), b1 / b2
  * fp32 [c].  The hidden tensor lives only in shared memory.  ctta_resblock_pair_supported() tells whether a
  * (c, taps, dilation) fits (c in {32, 64}, odd taps <= 11, even t for c = 32, resident weights + tiles within 227 KiB); otherwise the two
- * convolutions run through ctta_gemm.  Returns CTTA_ERR_UNSUPPORTED for an unsupported combination. */
+ * convolutions run through ctta_gemm.  Returns CTTA_ERR_UNSUPPORTED for an unsupported combination.  x_lrelu is read
+ * twice (halo'd TMA boxes for c1, and the residual rows through the read-only data path) and must not overlap out;
+ * the result is bit-identical to the two ctta_gemm launches. */
 int ctta_resblock_pair_supported(int32_t c, int32_t taps, int32_t dilation, int32_t t);
 int ctta_resblock_pair(const void* x_lrelu, void* out, int32_t dtype, int32_t batch, int32_t t, int32_t c, const void* w1,
                        const float* b1, const void* w2, const float* b2, int32_t taps, int32_t dilation, float slope,

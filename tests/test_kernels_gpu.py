@@ -241,6 +241,42 @@ def test_conv1d_time_folded(c, k, fold, t, bsz):
     assert rel(out2, direct) < 1e-3
 
 
+@pytest.mark.parametrize("c,k,dil,t,bsz", [(64, 3, 1, 40000, 3), (64, 7, 3, 20000, 3), (32, 3, 5, 60000, 3), (32, 11, 5, 50000, 2)])
+def test_resblock_pair_bit_identical_to_two_launches_and_reproducible(c, k, dil, t, bsz):
+    """Many tiles per CTA (the two-slot pipeline in steady state): every launch gives the same bits, and those bits are the
+    two-launch ctta_gemm path's (same products, same fp32 operation order in the epilogue)."""
+    torch.manual_seed(c + k + dil)
+    lx = F.leaky_relu(torch.randn(bsz, t, c, device=DEV), 0.1).to(DT)
+    w1 = torch.randn(c, c, k, device=DEV) / math.sqrt(k * c)
+    w2 = torch.randn(c, c, k, device=DEV) / math.sqrt(k * c)
+    b1, b2 = torch.randn(c, device=DEV) * 0.1, torch.randn(c, device=DEV) * 0.1
+    pw1, pw2 = ops.pack_conv1d(w1, b1, dilation=dil), ops.pack_conv1d(w2, b2, dilation=1)
+    tmp, two = torch.empty_like(lx), torch.empty_like(lx)
+    ops.conv1d(lx, pw1, out2=tmp, act2=ops.ACT_LRELU, act2_slope=0.1)
+    ops.conv1d(tmp, pw2, residual=lx, res_neg_scale=10.0, out2=two, act2=ops.ACT_LRELU, act2_slope=0.1)
+    first = ops.resblock_pair(lx, pw1, pw2, 0.1).clone()
+    assert torch.equal(first, two)
+    for _ in range(25):
+        assert torch.equal(ops.resblock_pair(lx, pw1, pw2, 0.1), first)
+
+
+def test_resblock_pair_input_aligned_to_16_bytes_only():
+    """The residual rows are read with 256-bit loads when the input is 32-byte aligned, else with 128-bit loads."""
+    torch.manual_seed(3)
+    c, k, t, bsz = 32, 7, 3000, 2
+    buf = torch.empty(bsz * t * c + 8, device=DEV, dtype=DT)
+    lx = buf[8:].view(bsz, t, c)
+    assert lx.data_ptr() % 32 == 16
+    lx.copy_(F.leaky_relu(torch.randn(bsz, t, c, device=DEV), 0.1))
+    w1 = torch.randn(c, c, k, device=DEV) / math.sqrt(k * c)
+    w2 = torch.randn(c, c, k, device=DEV) / math.sqrt(k * c)
+    b = torch.randn(c, device=DEV) * 0.1
+    pw1, pw2 = ops.pack_conv1d(w1, b, dilation=3), ops.pack_conv1d(w2, b, dilation=1)
+    aligned = lx.clone()
+    assert aligned.data_ptr() % 32 == 0
+    assert torch.equal(ops.resblock_pair(lx, pw1, pw2, 0.1), ops.resblock_pair(aligned, pw1, pw2, 0.1))
+
+
 def test_resblock_pair_unsupported_shapes_are_refused():
     assert not ops.resblock_pair_supported(64, 11, 1)        # resident weights of both convs exceed shared memory
     assert not ops.resblock_pair_supported(128, 3, 1) and not ops.resblock_pair_supported(32, 4, 1) and not ops.resblock_pair_supported(32, 3, 1, 1001)
