@@ -61,7 +61,8 @@ def main():
 
     orig = {}
     for name in ("gemm", "groupnorm_stats", "groupnorm_apply", "layernorm", "attention", "softmax_rows", "im2col_s2",
-                 "small_linear", "wave_to_int16", "nchw_to_nhwc", "nhwc_to_nchw", "time_features", "tap_sum", "mrf_combine"):
+                 "small_linear", "wave_to_int16", "nchw_to_nhwc", "nhwc_to_nchw", "time_features", "tap_sum", "mrf_combine",
+                 "resblock_pair"):
         orig[name] = getattr(ops, name)
         setattr(ops, name, wrap(name, orig[name], d_gemm if name == "gemm" else d_generic))
     # stage markers
