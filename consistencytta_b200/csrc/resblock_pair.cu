@@ -20,8 +20,15 @@
 // 128-row tile in both).  Tiles run through S "slots" (accumulators + H buffer), so that c1 of tile n + 1, E1 of tile
 // n + 1 and E2 of tile n overlap.
 //
-// These stages are bound by the ~60-cycle issue floor of tcgen05.mma at N <= 64 (profiles/r1_umma_rate_microbench.txt),
-// not by HBM: the fusion removes the second launch's epilogue / HBM round trip, the MMA count stays.
+// Shared-memory plan per shape (host side below): two slots wherever they fit, X ring 1-3 deep, and 0 / 1 / 2 own output
+// staging buffers (with own buffers the hidden-tile slot is released by the issuer's tcgen05.commit after c2; without,
+// the output is staged in the slot itself and released by the E2 warps once their TMA stores have read it).
+//
+// What bounds it (tools/trace_pair.py, profiles/r2_resblock_pair.txt): not HBM.  The MMA count is that of the two-launch
+// path (~45-60 cycles per tcgen05.mma at N <= 64: every instruction re-reads a 128 x 16 A slice from shared memory); at
+// C = 32 the E2 warp set is the longest stage (~2000 of ~2400 cycles per tile at k = 3), at C = 64 the residual loads
+// (thread == row puts the lanes of a warp 128 B apart: 32 distinct lines per load instruction).  Per pair it runs 1.2-1.9 x
+// faster than two launches, bit-identically.
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
