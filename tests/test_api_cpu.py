@@ -317,3 +317,14 @@ def test_scheduler_input_scale_works_for_foreign_scheduler_objects():
     d = DDIMScheduler.from_pretrained()
     d.set_timesteps(18)
     assert scheduler_input_scale(Foreign(d), d.timesteps[0]) == 1.0
+
+
+def test_fuse_pairs_switch_reads_zero_as_off(monkeypatch):
+    """CTTA_FUSE_PAIRS is an A/B switch of the vocoder (fused ResBlock-pair kernel, default on): "0" and "" mean off."""
+    from consistencytta_b200.vae import Generator
+    for val, want in ((None, True), ("1", True), ("0", False), ("", False)):
+        if val is None:
+            monkeypatch.delenv("CTTA_FUSE_PAIRS", raising=False)
+        else:
+            monkeypatch.setenv("CTTA_FUSE_PAIRS", val)
+        assert Generator().fuse_pairs is want
